@@ -1,0 +1,149 @@
+/*
+ * b200_lite_kernels.h -- C ABI of libb200lite.so, the B200 (sm_100a) kernel layer that stands in
+ * for `lite_llama.kernels` (reference: /root/reference/lite_llama/kernels/__init__.py:11-39).
+ *
+ * The reference has no FFI: its boundary is Python name binding (`from ..kernels import ...`,
+ * lite_llama/models/base.py:31-38, lite_llama/executor/model_runner.py:22,
+ * lite_llama/models/quantization/methods/*.py).  Each entry point below is what a ctypes binding
+ * for one of those names calls; lite_llama_b200/kernels/ holds that binding with the reference's
+ * exact Python signatures, INTEGRATION.md shows how to bind them inside the unmodified reference.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory;
+ *   - no entry point allocates, synchronises or touches the default stream: work is enqueued on
+ *     `stream` (a cudaStream_t) and is CUDA-graph capturable;
+ *   - strides are in ELEMENTS of the tensor's dtype; the innermost dimension must be contiguous;
+ *   - `dtype`: B2L_F16 / B2L_BF16 activation dtype (the reference is fp16-only);
+ *   - `*_width`: 4 or 8, byte width of an index vector (callers pass int32 or int64 vectors for
+ *     b_seq_len / b_req_idx / b_start_loc);
+ *   - return 0 on success, negative on error (B2L_ERR_*); b2l_last_error() returns a thread-local
+ *     message.  The Python shim turns non-zero returns into ValueError, mirroring the reference's
+ *     error behaviour (e.g. kernels/quantization/w4a16.py:174-184);
+ *   - workspaces: `b2l_*_workspace_bytes` are pure functions of shapes (+ SM count), so the caller
+ *     can size a torch.empty scratch buffer outside graph capture.  Split-K GEMMs additionally take a
+ *     small int32 `counters` array that must be ZERO on entry; kernels leave it zero on exit.
+ */
+#ifndef B200_LITE_KERNELS_H
+#define B200_LITE_KERNELS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2L_F16 0
+#define B2L_BF16 1
+
+#define B2L_OK 0
+#define B2L_ERR_INVALID (-1)
+#define B2L_ERR_CUDA (-2)
+#define B2L_ERR_UNSUPPORTED (-3)
+
+/* quantised-weight kinds for b2l_quant_gemm_workspace_bytes */
+#define B2L_Q_INT4 0
+#define B2L_Q_FP8 1
+#define B2L_Q_INT8 2
+
+const char* b2l_last_error(void);
+int b2l_version(void);
+int b2l_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
+
+/* skip_rmsnorm(X, residual, weight, eps) -- lite_llama/kernels/skip_rmsnorm.py:192-234.
+ * residual (nullable) is updated in place with x + residual (rounded to dtype); y gets
+ * round(sum_f32 * rrms) * weight. */
+int b2l_skip_rmsnorm(void* y, const void* x, void* residual, const void* weight, int64_t rows, int64_t n,
+                     int64_t x_row_stride, int64_t r_row_stride, int64_t y_row_stride, float eps, int dtype,
+                     void* stream);
+
+/* rope_emb_forward(q, k, cos, sin, batch_size, seq_len) -- lite_llama/kernels/rope_emb.py:86-134.
+ * In place on q [B*S, n_qh, D] and k [B*S, n_kh, D]; cos/sin [B, S, >=D/2] (first D/2 entries read). */
+int b2l_rope_emb(void* q, void* k, const void* cos, const void* sin, int64_t batch, int64_t seq_len, int n_qh,
+                 int n_kh, int head_dim, int64_t q_tok_stride, int64_t q_head_stride, int64_t k_tok_stride,
+                 int64_t k_head_stride, int64_t cs_batch_stride, int64_t cs_seq_stride, int dtype, void* stream);
+
+/* swiglu_forward(a, b) -- lite_llama/kernels/swiglu.py:45-65; also fused_moe's _silu_and_mul
+ * (lite_llama/kernels/fused_moe.py:296-313) by pointing b at the second half of each row. */
+int b2l_swiglu(void* c, const void* a, const void* b, int64_t rows, int64_t n, int64_t a_row_stride,
+               int64_t b_row_stride, int64_t c_row_stride, int dtype, void* stream);
+
+/* update_kv_buffer(KV_Values, Select_Index, KV_Buffer) -- lite_llama/kernels/update_kv_buffer.py:55-89.
+ * Heads [0, heads_a) of every destination row come from src_a, heads [heads_a, heads_a+heads_b) from
+ * src_b (so K and V need no torch.cat, lite_llama/models/base.py:76); pass heads_b = 0 for one source.
+ * 2-byte element dtype. */
+int b2l_update_kv_buffer(const void* src_a, const void* src_b, const void* select_index, int index_width,
+                         void* kv_buffer, int64_t tokens, int heads_a, int heads_b, int head_dim,
+                         int64_t a_tok_stride, int64_t a_head_stride, int64_t b_tok_stride, int64_t b_head_stride,
+                         int64_t d_tok_stride, int64_t d_head_stride, void* stream);
+
+/* update_kv_index(req_to_token_indexs, b_req_idx, b_seq_len, select_index)
+ * -- lite_llama/kernels/update_kv_index.py:51-88.  table is int32. */
+int b2l_update_kv_index(void* table, const void* b_req_idx, int req_width, const void* b_seq_len, int len_width,
+                        const void* select_index, int sel_width, int64_t n, int64_t stride_b, int64_t stride_s,
+                        void* stream);
+
+/* flash_decoding(q, k_cache, v_cache, qk_scale, b_req_tokens_table, b_req_idx, b_seq_len,
+ * max_actual_seq_len) -- lite_llama/kernels/flashdecoding.py:316-380. */
+int64_t b2l_flash_decoding_workspace_bytes(int64_t batch, int num_q_heads, int num_kv_heads, int head_dim,
+                                           int64_t max_seq_len);
+int b2l_flash_decoding(void* out, const void* q, const void* k_cache, const void* v_cache,
+                       const void* b_req_tokens_table, const void* b_req_idx, int req_idx_width,
+                       const void* b_seq_len, int seq_len_width, int64_t batch, int num_q_heads, int num_kv_heads,
+                       int head_dim, int64_t max_seq_len, float qk_scale, int64_t q_batch_stride,
+                       int64_t q_head_stride, int64_t k_token_stride, int64_t k_head_stride, int64_t v_token_stride,
+                       int64_t v_head_stride, int64_t table_batch_stride, int64_t table_seq_stride,
+                       int64_t o_batch_stride, int64_t o_head_stride, void* workspace, int64_t workspace_bytes,
+                       int dtype, void* stream);
+
+/* flash_attention2_no_pad(q, k, v, sm_scale, b_start_loc, b_seq_len, max_seq_len)
+ * -- lite_llama/kernels/flashattention2_nopad.py:175-231.  sm_scale already carries log2(e). */
+int b2l_flash_attention2_no_pad(void* out, const void* q, const void* k, const void* v, const void* b_start_loc,
+                                int start_loc_width, const void* b_seq_len, int seq_len_width, int64_t batch,
+                                int num_q_heads, int num_kv_heads, int head_dim, int64_t max_seq_len,
+                                float sm_scale_log2, int64_t q_tok_stride, int64_t q_head_stride,
+                                int64_t k_tok_stride, int64_t k_head_stride, int64_t v_tok_stride,
+                                int64_t v_head_stride, int64_t o_tok_stride, int64_t o_head_stride, int dtype,
+                                void* stream);
+
+/* Dense projection y = x @ w.T (+ bias): the reference's F.linear call sites
+ * (lite_llama/models/quantization/methods/unquantized.py:21-22, lite_llama/models/base.py:489). */
+int64_t b2l_linear_workspace_bytes(int64_t m, int64_t n, int64_t k, int elem_bytes);
+int64_t b2l_linear_num_counters(int64_t m, int64_t n);
+int b2l_linear(void* y, const void* x, const void* w, const void* bias, int64_t m, int64_t n, int64_t k,
+               int64_t x_row_stride, int64_t w_row_stride, int64_t y_row_stride, void* workspace,
+               int64_t workspace_bytes, void* counters, int64_t num_counters, int dtype, void* stream);
+
+/* w4a16_matmul(x, qweight, scales, zeros, *, group_size, bias)
+ * -- lite_llama/kernels/quantization/w4a16.py:152-207.  fp16 activations only (w4a16.py:174). */
+int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k);
+int64_t b2l_quant_gemm_num_counters(int64_t m, int64_t n);
+int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, const void* scales, const void* zeros,
+                     const void* bias, int bias_is_f32, int64_t m, int64_t n, int64_t k, int group_size,
+                     int64_t x_row_stride, int64_t qw_row_stride, int64_t s_row_stride, int64_t s_col_stride,
+                     int64_t y_row_stride, void* workspace, int64_t workspace_bytes, void* counters,
+                     int64_t num_counters, void* stream);
+
+/* w8a16_matmul(x, qweight, scales, *, group_n, group_k, bias)
+ * -- lite_llama/kernels/quantization/w8a16.py:155-216.  qweight uint8 (fp8-e4m3 bits) or int8. */
+int b2l_w8a16_matmul(void* y, const void* x, const void* qweight, int weight_is_fp8, const void* scales,
+                     const void* bias, int bias_is_f32, int64_t m, int64_t n, int64_t k, int64_t group_n,
+                     int64_t group_k, int64_t x_row_stride, int64_t qw_row_stride, int64_t s_row_stride,
+                     int64_t s_col_stride, int64_t y_row_stride, void* workspace, int64_t workspace_bytes,
+                     void* counters, int64_t num_counters, void* stream);
+
+/* smoothquant_matmul(x, qweight, weight_scales, *, bias) -- lite_llama/kernels/quantization/w8a8.py:151-217
+ * is two calls: per-token dynamic quantisation (w8a8.py:35-68), then the int8 GEMM (w8a8.py:75-130). */
+int b2l_quantize_activations_int8(void* q, void* scales, const void* x, int64_t m, int64_t k, int64_t x_row_stride,
+                                  int64_t q_row_stride, int dtype, void* stream);
+int b2l_w8a8_gemm(void* y, const void* xq, const void* wq, const void* a_scale, const void* b_scale,
+                  const void* bias_f32, int64_t m, int64_t n, int64_t k, int64_t xq_row_stride,
+                  int64_t wq_row_stride, int64_t y_row_stride, void* workspace, int64_t workspace_bytes,
+                  void* counters, int64_t num_counters, int out_dtype, void* stream);
+
+/* fused_moe pieces -- lite_llama/kernels/fused_moe.py:45-99 (align), :316-333 (sum). */
+int b2l_moe_sum(void* out, const void* in, int64_t tokens, int64_t n, int top_k, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_LITE_KERNELS_H */

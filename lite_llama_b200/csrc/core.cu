@@ -1,0 +1,55 @@
+// Library-wide plumbing: thread-local error string, device attribute cache, version.
+#include "common.cuh"
+#include <string.h>
+
+static thread_local char g_err[512] = {0};
+
+void b2l_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* b2l_last_error(void) { return g_err; }
+extern "C" int b2l_version(void) { return 100; }
+
+static int g_sms[64] = {0};
+static int g_smem[64] = {0};
+
+int b2l_num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (g_sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    g_sms[dev] = v;
+  }
+  return g_sms[dev];
+}
+
+int b2l_max_smem_optin() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 227 * 1024;
+  if (g_smem[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0)
+      v = 227 * 1024;
+    g_smem[dev] = v;
+  }
+  return g_smem[dev];
+}
+
+extern "C" int b2l_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin) {
+  int dev = 0;
+  B2L_CUDA_CHECK(cudaGetDevice(&dev));
+  int v = 0;
+  if (sm_count) { B2L_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+  if (cc_major) { B2L_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+  if (cc_minor) { B2L_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+  if (max_smem_optin) {
+    B2L_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    *max_smem_optin = v;
+  }
+  return B2L_OK;
+}

@@ -1,0 +1,31 @@
+"""B200 kernels behind the ``lite_llama.kernels`` names
+(reference export list: lite_llama/kernels/__init__.py:22-39).
+
+Every callable keeps the reference's signature and argument meaning; all of them launch
+hand-written sm_100a CUDA from ``libb200lite.so`` on the current CUDA stream.
+"""
+
+from .flashattention2_nopad import flash_attention2_no_pad
+from .flashdecoding import flash_decoding
+from .linear import linear
+from .rope_emb import rope_emb_forward
+from .skip_rmsnorm import skip_rmsnorm
+from .swiglu import swiglu_forward
+from .update_kv_buffer import update_kv_buffer, update_kv_buffer_split
+from .update_kv_index import update_kv_index
+from .quantization import smoothquant_matmul, w4a16_matmul, w8a16_matmul
+
+__all__ = [
+    "flash_attention2_no_pad",
+    "flash_decoding",
+    "linear",
+    "rope_emb_forward",
+    "skip_rmsnorm",
+    "swiglu_forward",
+    "update_kv_buffer",
+    "update_kv_buffer_split",
+    "update_kv_index",
+    "w4a16_matmul",
+    "w8a16_matmul",
+    "smoothquant_matmul",
+]

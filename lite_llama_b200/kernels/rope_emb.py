@@ -1,0 +1,35 @@
+"""Half-split RoPE on q and k, in place (reference: lite_llama/kernels/rope_emb.py:86-134)."""
+
+from __future__ import annotations
+
+import torch
+
+from ._common import check, dtype_code, lib, require_cuda, stream_handle
+
+
+@torch.no_grad()
+def rope_emb_forward(q, k, cos, sin, batch_size, seq_len):
+    """Rotate ``q [B*S, Hq, D]`` and ``k [B*S, Hkv, D]`` by ``cos/sin [B, S, D]`` (first D/2 read).
+
+    Like the reference, non-contiguous inputs are made contiguous first (so a strided ``k`` view is
+    copied, rope_emb.py:106-107) and the returned tensors are the ones to use.
+    """
+    require_cuda(q, k, cos, sin)
+    n, n_qh, hd = q.shape
+    _, n_kh, _ = k.shape
+    assert batch_size * seq_len == n
+    code = dtype_code(q, "q")
+    q = q.contiguous()
+    k = k.contiguous()
+    cos = cos.contiguous()
+    sin = sin.contiguous()
+    if cos.dtype != q.dtype:  # the reference computes in the cos/sin dtype; the caller casts to x.dtype
+        cos = cos.to(q.dtype)
+        sin = sin.to(q.dtype)
+    check(
+        lib().b2l_rope_emb(
+            q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(), batch_size, seq_len, n_qh, n_kh, hd,
+            q.stride(0), q.stride(1), k.stride(0), k.stride(1), cos.stride(0), cos.stride(1), code, stream_handle(),
+        )
+    )
+    return q, k

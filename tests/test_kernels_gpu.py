@@ -1,0 +1,512 @@
+"""Parity tests proper: the sm_100a CUDA kernels (through the C ABI / ctypes shims) against
+(1) the golden outputs recorded from the reference's own Triton kernels and (2) the CPU oracle on
+seeded random inputs, on the case lists of the reference's tests/kernels/*.py, plus the
+reference-free invariants those tests use.
+
+Tolerances (stated per op, always tighter than or equal to the reference's own test tolerances):
+  integer / index results ......... bit-exact
+  norm / swiglu / rope ............ 2 fp16 ulp (rtol 2e-3, atol 1e-3 [rope: 4e-3 for |x| up to 8])
+  attention ....................... rtol 2e-3, atol 2e-3   (reference tests: 1e-2 .. 2e-2)
+  GEMMs (dense, w4a16, w8a16, w8a8) rtol 2e-3, atol 2e-3 on O(1) outputs (reference: 1e-2 .. 1e-1)
+"""
+
+from __future__ import annotations
+
+import math
+
+import pytest
+import torch
+
+from b2l_testutil import load_golden, to_cuda
+from oracle import ops
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
+
+LOG2E = 1.4426950408889634
+TOL = dict(rtol=2e-3, atol=1e-3)
+ATT_TOL = dict(rtol=2e-3, atol=2e-3)
+GEMM_TOL = dict(rtol=2e-3, atol=2e-3)
+
+
+def K():
+    import lite_llama_b200.kernels as k
+
+    return k
+
+
+def close(actual, expected, **tol):
+    torch.testing.assert_close(actual.float().cpu(), expected.float().cpu(), **(tol or TOL))
+
+
+# --------------------------------------------------------------------------- #
+# skip_rmsnorm
+# --------------------------------------------------------------------------- #
+def test_skip_rmsnorm_golden():
+    for c in load_golden("skip_rmsnorm")["cases"]:
+        g = to_cuda(c)
+        res = None if g["residual"] is None else g["residual"].clone()
+        y, r = K().skip_rmsnorm(g["x"].clone(), res, g["weight"], g["eps"])
+        close(y, c["y"])
+        if c["residual"] is not None:
+            assert torch.equal(r.cpu(), c["residual_out"])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 64), (2, 5, 896), (3, 7, 4096), (4, 1, 3584), (2, 3, 100), (1, 2, 8192)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_skip_rmsnorm_matches_oracle(shape, dtype):
+    x = torch.randn(shape, device="cuda", dtype=dtype)
+    r = torch.randn(shape, device="cuda", dtype=dtype)
+    w = torch.randn(shape[-1], device="cuda", dtype=dtype)
+    y_ref, r_ref = ops.skip_rmsnorm(x.cpu(), r.cpu(), w.cpu(), 1e-5)
+    r_in = r.clone()
+    y, r_out = K().skip_rmsnorm(x, r_in, w, 1e-5)
+    tol = TOL if dtype == torch.float16 else dict(rtol=1.6e-2, atol=8e-3)
+    close(y, y_ref, **tol)
+    assert torch.equal(r_out.cpu(), r_ref)
+    assert r_out.data_ptr() == r_in.data_ptr(), "residual must be updated in place and returned aliased"
+    y2, x_back = K().skip_rmsnorm(x, None, w, 1e-5)
+    close(y2, ops.rmsnorm(x.cpu(), w.cpu(), 1e-5), **tol)
+    assert x_back.data_ptr() == x.data_ptr()
+
+
+def test_skip_rmsnorm_per_head_layout():
+    # the Qwen3 q/k-norm call: [tokens, heads, head_dim] normalised over head_dim (models/base.py:222-225)
+    x = torch.randn(7, 14, 128, device="cuda", dtype=torch.float16)
+    w = torch.randn(128, device="cuda", dtype=torch.float16)
+    y, _ = K().skip_rmsnorm(x, None, w, 1e-6)
+    close(y, ops.rmsnorm(x.cpu(), w.cpu(), 1e-6))
+
+
+def test_skip_rmsnorm_known_answer():
+    x = torch.full((2, 3, 64), 2.0, device="cuda", dtype=torch.float16)
+    r = torch.full((2, 3, 64), 3.0, device="cuda", dtype=torch.float16)
+    w = (torch.arange(64, device="cuda") / 64).half()
+    y, res = K().skip_rmsnorm(x, r, w, 1e-6)
+    close(y, w.expand(2, 3, 64))
+    assert (res == 5).all()
+
+
+# --------------------------------------------------------------------------- #
+# swiglu / rope
+# --------------------------------------------------------------------------- #
+def test_swiglu_golden_and_oracle():
+    for c in load_golden("swiglu")["cases"]:
+        g = to_cuda(c)
+        close(K().swiglu_forward(g["a"], g["b"]), c["out"])
+    for shape in [(1, 1, 14336), (2, 3, 18944), (5, 100)]:
+        a = torch.randn(shape, device="cuda", dtype=torch.float16) * 3
+        b = torch.randn(shape, device="cuda", dtype=torch.float16)
+        close(K().swiglu_forward(a, b), ops.swiglu(a.cpu(), b.cpu()))
+    z = torch.zeros(4, 256, device="cuda", dtype=torch.float16)
+    assert (K().swiglu_forward(z, torch.randn_like(z)) == 0).all(), "zero gate must give zero"
+
+
+def test_rope_golden_bit_exact_where_the_interpreter_agrees():
+    # the kernel contracts mul+fma exactly like Triton's sm_100 codegen; the interpreter rounds each
+    # op, so allow 1 ulp at |x| < 8 against the golden and 2 ulp against the fp32 oracle
+    for c in load_golden("rope")["cases"]:
+        g = to_cuda(c)
+        q, k = K().rope_emb_forward(g["q"].clone(), g["k"].clone(), g["cos"], g["sin"], c["batch"], c["seq"])
+        close(q, c["q_out"], rtol=2e-3, atol=4e-3)
+        close(k, c["k_out"], rtol=2e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("hd", [32, 64, 128])
+def test_rope_matches_oracle_and_is_in_place(hd):
+    b, s, hq, hk = 2, 9, 8, 2
+    q = torch.randn(b * s, hq, hd, device="cuda", dtype=torch.float16)
+    k = torch.randn(b * s, hk, hd, device="cuda", dtype=torch.float16)
+    ang = torch.rand(b, s, hd // 2, device="cuda") * 6.28
+    cos = torch.cat([ang.cos(), ang.cos()], -1).half()
+    sin = torch.cat([ang.sin(), ang.sin()], -1).half()
+    q_ref = ops.rope_half_split(q.cpu(), cos.cpu(), sin.cpu(), b, s)
+    k_ref = ops.rope_half_split(k.cpu(), cos.cpu(), sin.cpu(), b, s)
+    q_in, k_in = q.clone(), k.clone()
+    qo, ko = K().rope_emb_forward(q_in, k_in, cos, sin, b, s)
+    close(qo, q_ref, rtol=2e-3, atol=4e-3)
+    close(ko, k_ref, rtol=2e-3, atol=4e-3)
+    assert qo.data_ptr() == q_in.data_ptr() and ko.data_ptr() == k_in.data_ptr()
+    # zero angle is the identity (tests/kernels/test_rope_emb.py:80-96)
+    one, zero = torch.ones_like(cos), torch.zeros_like(sin)
+    q2, _ = K().rope_emb_forward(q.clone(), k.clone(), one, zero, b, s)
+    assert torch.equal(q2, q)
+    # rotation preserves the pairwise norm
+    n0 = (q[..., : hd // 2].float() ** 2 + q[..., hd // 2 :].float() ** 2)
+    n1 = (qo[..., : hd // 2].float() ** 2 + qo[..., hd // 2 :].float() ** 2)
+    torch.testing.assert_close(n0, n1, rtol=1e-2, atol=1e-2)
+
+
+# --------------------------------------------------------------------------- #
+# KV cache ops (bit-exact)
+# --------------------------------------------------------------------------- #
+def test_kv_ops_golden():
+    g = load_golden("kv_ops")
+    c = to_cuda(g)
+    buf = c["buffer"].clone()
+    K().update_kv_buffer(c["values"], c["select"], buf)
+    assert torch.equal(buf.cpu(), g["buffer_out"])
+    table = c["table"].clone()
+    K().update_kv_index(table, c["b_req_idx"], c["b_seq_len"], c["select_index"])
+    assert torch.equal(table.cpu(), g["table_out"])
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+def test_update_kv_buffer_strided_pool_and_untouched_rows(idx_dtype):
+    hkv, d, tokens, pool_rows = 4, 128, 37, 300
+    pool = torch.randn(pool_rows, 2 * hkv, d, device="cuda", dtype=torch.float16)
+    before = pool.clone()
+    vals = torch.randn(tokens, 2 * hkv, d, device="cuda", dtype=torch.float16)
+    sel = torch.randperm(pool_rows, device="cuda")[:tokens].to(idx_dtype if idx_dtype == torch.int64 else torch.int32)
+    K().update_kv_buffer(vals, sel, pool)
+    expect = ops.update_kv_buffer(vals.cpu(), sel.cpu(), before.cpu())
+    assert torch.equal(pool.cpu(), expect)
+    # split K/V sources written without torch.cat
+    pool2 = before.clone()
+    xkv = torch.randn(tokens, 2 * hkv * d, device="cuda", dtype=torch.float16)
+    xk, xv = torch.split(xkv, hkv * d, dim=-1)
+    K().update_kv_buffer_split(xk.view(tokens, hkv, d), xv.view(tokens, hkv, d), sel, pool2)
+    expect2 = ops.update_kv_buffer(xkv.view(tokens, 2 * hkv, d).cpu(), sel.cpu(), before.cpu())
+    assert torch.equal(pool2.cpu(), expect2)
+
+
+@pytest.mark.parametrize("dt", [torch.int32, torch.int64])
+def test_update_kv_index_both_index_widths(dt):
+    table = torch.zeros(8, 64, dtype=torch.int32, device="cuda")
+    req = torch.tensor([5, 0, 7, 2], device="cuda", dtype=dt)
+    lens = torch.tensor([1, 64, 33, 2], device="cuda", dtype=dt)
+    sel = torch.tensor([11, 22, 33, 44], device="cuda", dtype=torch.int32)
+    K().update_kv_index(table, req, lens, sel)
+    expect = ops.update_kv_index(torch.zeros(8, 64, dtype=torch.int32), req.cpu(), lens.cpu(), sel.cpu())
+    assert torch.equal(table.cpu(), expect)
+
+
+# --------------------------------------------------------------------------- #
+# flash_decoding
+# --------------------------------------------------------------------------- #
+_MAX_TOKENS = 2048
+
+
+def _decode_case(seq_lens, hq, hkv, d, *, scattered=False, req_idx=None, dtype=torch.float16, idx=torch.int32,
+                 fused_pool=False):
+    q = torch.randn(len(seq_lens), hq, d, device="cuda", dtype=dtype) * 0.3
+    width = max(seq_lens)
+    nslots = len(seq_lens)
+    rows = max(_MAX_TOKENS, nslots * width)
+    if fused_pool:
+        pool = torch.randn(rows, 2 * hkv, d, device="cuda", dtype=dtype)
+        kc, vc = pool[:, :hkv], pool[:, hkv:]
+    else:
+        kc = torch.randn(rows, hkv, d, device="cuda", dtype=dtype)
+        vc = torch.randn(rows, hkv, d, device="cuda", dtype=dtype)
+    table = torch.zeros(nslots, width, dtype=torch.int32, device="cuda")
+    if scattered:
+        perm = torch.randperm(rows, device="cuda").to(torch.int32)
+        for i in range(nslots):
+            table[i] = perm[i * width : (i + 1) * width]
+    else:
+        for i in range(nslots):
+            table[i] = torch.arange(i * width, (i + 1) * width, dtype=torch.int32, device="cuda")
+    b_seq = torch.tensor(seq_lens, dtype=idx, device="cuda")
+    b_req = torch.arange(nslots, dtype=idx, device="cuda") if req_idx is None else torch.tensor(req_idx, dtype=idx, device="cuda")
+    scale = 1.0 / math.sqrt(d)
+    out = K().flash_decoding(q, kc, vc, scale, table, b_req, b_seq, width)
+    ref = ops.paged_decode_attention(q.cpu(), kc.cpu(), vc.cpu(), table.cpu(), b_req.cpu(), b_seq.cpu(), scale)
+    return out, ref
+
+
+def test_flash_decoding_golden():
+    for c in load_golden("flash_decoding")["cases"]:
+        g = to_cuda(c)
+        out = K().flash_decoding(g["q"], g["k_cache"], g["v_cache"], c["scale"], g["table"], g["b_req_idx"],
+                                 g["b_seq_len"], c["max_len"])
+        close(out, c["out"], **ATT_TOL)
+
+
+@pytest.mark.parametrize("seq_lens", [[1], [15], [16], [17], [63], [64], [65], [128], [129], [255], [256], [257], [1000]])
+def test_flash_decoding_boundaries(seq_lens):
+    out, ref = _decode_case(seq_lens, 4, 4, 64)
+    assert torch.isfinite(out).all()
+    close(out, ref, **ATT_TOL)
+
+
+@pytest.mark.parametrize("seq_lens", [[32, 32], [1, 200], [17, 129, 64, 3], [700, 5, 1300, 64]])
+def test_flash_decoding_ragged(seq_lens):
+    out, ref = _decode_case(seq_lens, 4, 2, 64)
+    close(out, ref, **ATT_TOL)
+
+
+@pytest.mark.parametrize("hq,hkv", [(4, 4), (8, 2), (14, 2), (8, 1), (32, 8), (28, 4), (32, 1)])
+def test_flash_decoding_gqa_ratios(hq, hkv):
+    out, ref = _decode_case([48, 130], hq, hkv, 64)
+    close(out, ref, **ATT_TOL)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_flash_decoding_head_dims_and_dtypes(d, dtype):
+    out, ref = _decode_case([40, 150], 4, 2, d, dtype=dtype)
+    tol = ATT_TOL if dtype == torch.float16 else dict(rtol=1.6e-2, atol=1.6e-2)
+    close(out, ref, **tol)
+
+
+@pytest.mark.parametrize("seq_lens", [[64], [33, 130]])
+def test_flash_decoding_scattered_rows(seq_lens):
+    out, ref = _decode_case(seq_lens, 4, 2, 64, scattered=True)
+    close(out, ref, **ATT_TOL)
+
+
+def test_flash_decoding_slot_indirection_and_int64_indices():
+    out, ref = _decode_case([40, 24, 61], 8, 8, 64, req_idx=[2, 1, 0], idx=torch.int64)
+    close(out, ref, **ATT_TOL)
+    out, ref = _decode_case([33, 33, 33], 4, 2, 64, req_idx=[0, 1, 1])
+    close(out, ref, **ATT_TOL)
+
+
+def test_flash_decoding_on_the_fused_kv_pool_views():
+    # the model hands strided views kv[:, :Hkv], kv[:, Hkv:] of one pool (models/base.py:119-123)
+    out, ref = _decode_case([100, 300, 7], 32, 8, 128, fused_pool=True)
+    close(out, ref, **ATT_TOL)
+
+
+def test_flash_decoding_uniform_values():
+    d, n = 64, 150
+    q = torch.randn(1, 4, d, device="cuda", dtype=torch.float16) * 0.3
+    kc = torch.randn(_MAX_TOKENS, 4, d, device="cuda", dtype=torch.float16)
+    vc = torch.full((_MAX_TOKENS, 4, d), 0.25, device="cuda", dtype=torch.float16)
+    table = torch.arange(n, dtype=torch.int32, device="cuda").unsqueeze(0)
+    out = K().flash_decoding(q, kc, vc, 1 / math.sqrt(d), table, torch.zeros(1, dtype=torch.int32, device="cuda"),
+                             torch.tensor([n], dtype=torch.int32, device="cuda"), n)
+    close(out, torch.full_like(out, 0.25), **ATT_TOL)
+
+
+def test_flash_decoding_llama3_shape_long_context():
+    # BASELINE shape: B=32, Hq=32, Hkv=8, D=128; ragged contexts up to 2048
+    torch.manual_seed(1)
+    B, hq, hkv, d, ctx = 8, 32, 8, 128, 2048
+    pool_rows = B * ctx
+    pool = torch.randn(pool_rows, 2 * hkv, d, device="cuda", dtype=torch.float16)
+    kc, vc = pool[:, :hkv], pool[:, hkv:]
+    lens = torch.randint(ctx // 2, ctx + 1, (B,))
+    table = torch.arange(pool_rows, dtype=torch.int32, device="cuda").view(B, ctx)
+    q = torch.randn(B, hq, d, device="cuda", dtype=torch.float16) * 0.3
+    b_seq = lens.to(torch.int32).cuda()
+    b_req = torch.arange(B, dtype=torch.int32, device="cuda")
+    out = K().flash_decoding(q, kc, vc, 1 / math.sqrt(d), table, b_req, b_seq, ctx)
+    ref = ops.paged_decode_attention(q.cpu(), kc.cpu(), vc.cpu(), table.cpu(), b_req.cpu(), b_seq.cpu(), 1 / math.sqrt(d))
+    close(out, ref, **ATT_TOL)
+
+
+# --------------------------------------------------------------------------- #
+# flash_attention2_no_pad
+# --------------------------------------------------------------------------- #
+def _prefill_case(seq_lens, hq, hkv, d, dtype=torch.float16, padded_to=None, strided_kv=False):
+    if padded_to is None:
+        starts = [sum(seq_lens[:i]) for i in range(len(seq_lens))]
+        total = sum(seq_lens)
+    else:  # the engine's padded rectangle: sequence i starts at i*max_prompt_len (model_runner.py:153-179)
+        starts = [i * padded_to for i in range(len(seq_lens))]
+        total = padded_to * len(seq_lens)
+    q = torch.randn(total, hq, d, device="cuda", dtype=dtype) * 0.3
+    if strided_kv:
+        xkv = torch.randn(total, 2 * hkv * d, device="cuda", dtype=dtype) * 0.3
+        k, v = (t.view(total, hkv, d) for t in torch.split(xkv, hkv * d, dim=-1))
+    else:
+        k = torch.randn(total, hkv, d, device="cuda", dtype=dtype) * 0.3
+        v = torch.randn(total, hkv, d, device="cuda", dtype=dtype) * 0.3
+    b_start = torch.tensor(starts, dtype=torch.int32, device="cuda")
+    b_len = torch.tensor(seq_lens, dtype=torch.int32, device="cuda")
+    scale = 1.0 / math.sqrt(d)
+    out = K().flash_attention2_no_pad(q, k, v, scale * LOG2E, b_start, b_len, max(seq_lens))
+    ref = ops.varlen_causal_attention(q.cpu(), k.cpu(), v.cpu(), b_start.cpu(), b_len.cpu(), scale)
+    valid = torch.zeros(total, dtype=torch.bool)
+    for s, n in zip(starts, seq_lens):
+        valid[s : s + n] = True
+    return out.cpu()[valid], ref[valid], (q, k, v)
+
+
+def test_flash_attention_nopad_golden():
+    for c in load_golden("flash_attention_nopad")["cases"]:
+        g = to_cuda(c)
+        out = K().flash_attention2_no_pad(g["q"], g["k"], g["v"], c["scale"] * LOG2E, g["b_start_loc"],
+                                          g["b_seq_len"], c["max_len"])
+        valid = torch.zeros(c["q"].shape[0], dtype=torch.bool)
+        for s, n in zip(c["b_start_loc"].tolist(), c["b_seq_len"].tolist()):
+            valid[s : s + n] = True
+        close(out.cpu()[valid], c["out"][valid], **ATT_TOL)
+
+
+@pytest.mark.parametrize("seq_lens", [[16], [64], [100], [32, 32], [7, 100, 33], [1, 64], [129, 65, 200], [513]])
+def test_flash_attention_nopad_ragged(seq_lens):
+    out, ref, _ = _prefill_case(seq_lens, 4, 4, 64)
+    close(out, ref, **ATT_TOL)
+
+
+@pytest.mark.parametrize("hq,hkv", [(4, 4), (8, 2), (14, 2), (8, 1), (32, 8)])
+def test_flash_attention_nopad_gqa(hq, hkv):
+    out, ref, _ = _prefill_case([48, 24], hq, hkv, 64)
+    close(out, ref, **ATT_TOL)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_flash_attention_nopad_head_dims(d, dtype):
+    out, ref, _ = _prefill_case([40, 24], 4, 2, d, dtype=dtype)
+    tol = ATT_TOL if dtype == torch.float16 else dict(rtol=1.6e-2, atol=1.6e-2)
+    close(out, ref, **tol)
+
+
+def test_flash_attention_nopad_padded_rectangle_and_strided_kv():
+    out, ref, _ = _prefill_case([128, 90, 17], 32, 8, 128, padded_to=128, strided_kv=True)
+    close(out, ref, **ATT_TOL)
+
+
+def test_flash_attention_nopad_first_token_sees_only_itself():
+    d = 64
+    q = torch.randn(40, 4, d, device="cuda", dtype=torch.float16)
+    k = torch.randn(40, 4, d, device="cuda", dtype=torch.float16)
+    v = torch.randn(40, 4, d, device="cuda", dtype=torch.float16)
+    out = K().flash_attention2_no_pad(q, k, v, LOG2E / math.sqrt(d), torch.tensor([0, 25], dtype=torch.int32, device="cuda"),
+                                      torch.tensor([25, 15], dtype=torch.int32, device="cuda"), 25)
+    close(out[0], v[0], **ATT_TOL)
+    close(out[25], v[25], **ATT_TOL)  # no leak from the previous sequence
+
+
+# --------------------------------------------------------------------------- #
+# dense linear (tcgen05)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("m,n,k", [(1, 128, 64), (1, 256, 512), (8, 2048, 2048), (32, 4096, 4096), (33, 130, 384),
+                                   (128, 768, 1024), (200, 1000, 320), (300, 512, 4096), (32, 512, 14336)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_linear_matches_oracle(m, n, k, dtype):
+    x = torch.randn(m, k, device="cuda", dtype=dtype) * 0.5
+    w = torch.randn(n, k, device="cuda", dtype=dtype) * 0.05
+    out = K().linear(x, w)
+    ref = x.float().cpu() @ w.float().cpu().T
+    tol = GEMM_TOL if dtype == torch.float16 else dict(rtol=1.6e-2, atol=1.6e-2)
+    close(out, ref.to(dtype), **tol)
+
+
+def test_linear_bias_leading_dims_and_determinism():
+    x = torch.randn(2, 3, 4096, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(1024, 4096, device="cuda", dtype=torch.float16) * 0.05
+    b = torch.randn(1024, device="cuda", dtype=torch.float16)
+    out = K().linear(x, w, b)
+    assert out.shape == (2, 3, 1024)
+    close(out, ops.linear(x.cpu(), w.cpu(), b.cpu()), **GEMM_TOL)
+    # split-K reduction is ordered: bitwise reproducible
+    for _ in range(3):
+        assert torch.equal(K().linear(x, w, b), out)
+
+
+def test_linear_llama3_lm_head_slice():
+    x = torch.randn(32, 4096, device="cuda", dtype=torch.float16)
+    w = torch.randn(16032, 4096, device="cuda", dtype=torch.float16) * 0.02
+    out = K().linear(x, w)
+    close(out, (x.float() @ w.float().T).half(), **GEMM_TOL)
+
+
+# --------------------------------------------------------------------------- #
+# quantised GEMMs
+# --------------------------------------------------------------------------- #
+def test_w4a16_golden():
+    for c in load_golden("w4a16")["cases"]:
+        g = to_cuda(c)
+        out = K().w4a16_matmul(g["x"], g["qweight"], g["scales"], g["zeros"], group_size=c["group_size"], bias=g["bias"])
+        close(out, c["out"], **GEMM_TOL)
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 256, 512), (8, 512, 1024), (32, 4096, 4096), (33, 130, 384), (100, 256, 2048),
+                                   (32, 512, 14336)])
+@pytest.mark.parametrize("gs", [32, 128])
+def test_w4a16_matches_oracle(m, n, k, gs):
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k, dtype=torch.float32) * 0.05
+    qw, sc, zp = ops.quantize_int4_groupwise(w, gs)
+    out = K().w4a16_matmul(x, qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs)
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs), **GEMM_TOL)
+
+
+def test_w4a16_non_integer_zero_points_and_bias():
+    m, n, k, gs = 5, 256, 512, 128
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), dtype=torch.int64).to(torch.int32)
+    sc = torch.rand(n, k // gs) * 0.01 + 0.001
+    zp = torch.rand(n, k // gs) * 15
+    bias = torch.randn(n)
+    out = K().w4a16_matmul(x, qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs, bias=bias.cuda())
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs, bias), **GEMM_TOL)
+
+
+def test_w4a16_unpack_order_is_bit_exact():
+    # one-hot activations read single weights back: every (n, k) must land on nibble k%8 of word k//8
+    n, k, gs = 128, 128, 128
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), dtype=torch.int64).to(torch.int32)
+    x = torch.eye(k, dtype=torch.float16, device="cuda")
+    out = K().w4a16_matmul(x, qw.cuda(), torch.ones(n, 1, device="cuda"), torch.zeros(n, 1, device="cuda"), group_size=gs)
+    assert torch.equal(out.cpu().T.to(torch.int64), ops.unpack_int4(qw))
+
+
+def test_w8a16_golden():
+    for c in load_golden("w8a16")["cases"]:
+        x = c["x"].cuda()
+        for key in ("fp8_block", "int8_channel", "fp8_channel"):
+            d = c[key]
+            out = K().w8a16_matmul(x, d["qweight"].cuda(), d["scales"].cuda(), group_n=d["group_n"], group_k=d["group_k"])
+            close(out, d["out"], **GEMM_TOL)
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 512, 256), (8, 2048, 2048), (128, 768, 1024), (33, 130, 384)])
+def test_w8a16_matches_oracle(m, n, k):
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k) * 0.05
+    qw = w.to(torch.float8_e4m3fn).view(torch.uint8)
+    sc = torch.rand((n + 127) // 128, (k + 127) // 128) + 0.5
+    out = K().w8a16_matmul(x, qw.cuda(), sc.cuda(), group_n=128, group_k=128)
+    close(out, ops.w8a16_matmul(x.cpu(), qw, sc, 128, 128), **GEMM_TOL)
+    qi, si = ops.quantize_int8_per_channel(w)
+    out = K().w8a16_matmul(x, qi.cuda(), si.cuda(), group_n=1, group_k=k)
+    close(out, ops.w8a16_matmul(x.cpu(), qi, si, 1, k), **GEMM_TOL)
+
+
+def test_fp8_dequant_is_exact_for_every_code():
+    # each finite e4m3 code, read back through a one-hot activation, must equal its exact value
+    codes = torch.arange(256, dtype=torch.int32).to(torch.uint8)
+    qw = codes.repeat(128, 1)[:, :256].contiguous()              # [128, 256]
+    x = torch.eye(256, dtype=torch.float16, device="cuda")
+    out = K().w8a16_matmul(x, qw.cuda(), torch.ones(1, 1, device="cuda"), group_n=128, group_k=256)
+    finite = (codes & 0x7F) != 0x7F
+    expect = codes.view(torch.float8_e4m3fn).float()
+    assert torch.equal(out.cpu()[:, 0].float()[finite], expect[finite])
+
+
+def test_smoothquant_golden_and_quantiser_codes():
+    for c in load_golden("w8a8")["cases"]:
+        g = to_cuda(c)
+        out = K().smoothquant_matmul(g["x"], g["qweight"], g["weight_scales"], bias=g["bias"])
+        close(out, c["out"], rtol=2e-3, atol=1e-3)
+    from lite_llama_b200.kernels.quantization.w8a8 import quantize_activations_int8
+
+    x = torch.randn(64, 2048, device="cuda", dtype=torch.float16) * 0.5
+    q, s = quantize_activations_int8(x)
+    q_ref, s_ref = ops.quantize_activations_int8(x.cpu())
+    torch.testing.assert_close(s.cpu(), s_ref, rtol=1e-6, atol=0)
+    # div.full.f32 is within 2 ulp of IEEE division: codes may differ by one only at exact integers
+    diff = (q.cpu().int() - q_ref.int()).abs()
+    assert diff.max() <= 1 and (diff != 0).float().mean() < 1e-3
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 256, 512), (8, 512, 1024), (64, 2048, 2048), (256, 3584, 3584), (33, 130, 384)])
+def test_smoothquant_matches_oracle(m, n, k):
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k) * 0.05
+    scale = w.abs().amax(-1) / 127.0
+    qw = (w / scale.unsqueeze(-1)).round().clamp(-127, 127).to(torch.int8)
+    out = K().smoothquant_matmul(x, qw.cuda(), scale.cuda())
+    # compare on the kernel's own activation codes (they may differ from IEEE by one count at ties)
+    from lite_llama_b200.kernels.quantization.w8a8 import quantize_activations_int8
+
+    qa, sa = quantize_activations_int8(x)
+    acc = qa.cpu().to(torch.int64) @ qw.to(torch.int64).T
+    ref = (acc.float() * sa.cpu().unsqueeze(-1) * scale.unsqueeze(0)).half()
+    close(out, ref, rtol=1e-3, atol=5e-4)
+    close(out, ops.smoothquant_matmul(x.cpu(), qw, scale), rtol=2e-2, atol=2e-2)

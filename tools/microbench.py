@@ -1,0 +1,152 @@
+"""Per-kernel timing on the B200 (CUDA events, L2 flushed between iterations).
+
+Prints one JSON line per case with the achieved algorithmic GB/s (or TFLOP/s) and the fraction of
+the measured peak in MEASURED_PEAKS.json. Used to pick what to profile with ncu; the judged numbers
+come from bench.py.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import lite_llama_b200.kernels as K  # noqa: E402
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def timeit(fn, iters=20, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]  # median, ms
+
+
+def bench_decode(B, hq, hkv, d, ctx, scattered=False):
+    rows = B * ctx
+    pool = torch.randn(rows, 2 * hkv, d, device="cuda", dtype=torch.float16)
+    kc, vc = pool[:, :hkv], pool[:, hkv:]
+    if scattered:
+        table = torch.randperm(rows, device="cuda").to(torch.int32).view(B, ctx)
+    else:
+        table = torch.arange(rows, dtype=torch.int32, device="cuda").view(B, ctx)
+    q = torch.randn(B, hq, d, device="cuda", dtype=torch.float16)
+    b_seq = torch.full((B,), ctx, dtype=torch.int32, device="cuda")
+    b_req = torch.arange(B, dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: K.flash_decoding(q, kc, vc, 1 / math.sqrt(d), table, b_req, b_seq, ctx))
+    nbytes = B * ctx * 2 * hkv * d * 2
+    return {"op": "flash_decoding", "B": B, "Hq": hq, "Hkv": hkv, "D": d, "ctx": ctx, "scattered": scattered,
+            "ms": ms, "bytes": nbytes, "gbs": nbytes / ms / 1e6}
+
+
+def bench_gemm(kind, m, n, k):
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    if kind == "dense":
+        w = torch.randn(n, k, device="cuda", dtype=torch.float16) * 0.05
+        fn = lambda: K.linear(x, w)
+        nbytes = n * k * 2
+    elif kind == "torch":
+        w = torch.randn(n, k, device="cuda", dtype=torch.float16) * 0.05
+        fn = lambda: torch.nn.functional.linear(x, w)
+        nbytes = n * k * 2
+    elif kind == "w4a16":
+        qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), device="cuda", dtype=torch.int64).to(torch.int32)
+        sc = torch.rand(n, k // 128, device="cuda") * 0.01
+        zp = torch.full((n, k // 128), 8.0, device="cuda")
+        fn = lambda: K.w4a16_matmul(x, qw, sc, zp, group_size=128)
+        nbytes = n * k // 2 + n * (k // 128) * 8
+    elif kind == "w8a16":
+        qw = torch.randint(0, 120, (n, k), device="cuda", dtype=torch.uint8)
+        sc = torch.rand((n + 127) // 128, (k + 127) // 128, device="cuda")
+        fn = lambda: K.w8a16_matmul(x, qw, sc, group_n=128, group_k=128)
+        nbytes = n * k
+    elif kind == "w8a8":
+        qw = torch.randint(-127, 127, (n, k), device="cuda", dtype=torch.int8)
+        sc = torch.rand(n, device="cuda") * 0.01
+        fn = lambda: K.smoothquant_matmul(x, qw, sc)
+        nbytes = n * k
+    else:
+        raise ValueError(kind)
+    ms = timeit(fn)
+    flops = 2.0 * m * n * k
+    return {"op": kind, "m": m, "n": n, "k": k, "ms": ms, "bytes": nbytes, "gbs": nbytes / ms / 1e6,
+            "tflops": flops / ms / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="all")
+    args = ap.parse_args()
+    hbm, tf, src = peaks()
+    out = []
+    if args.which in ("all", "decode"):
+        for ctx in (256, 2048, 8192):
+            for sc in (False, True):
+                r = bench_decode(32, 32, 8, 128, ctx, sc)
+                r["frac_hbm"] = r["gbs"] / hbm
+                out.append(r)
+        r = bench_decode(1, 32, 8, 128, 256)
+        r["frac_hbm"] = r["gbs"] / hbm
+        out.append(r)
+    if args.which in ("all", "gemm"):
+        shapes = [(4096, 4096), (2048, 4096), (14336, 4096), (4096, 14336), (128256, 4096)]
+        for kind in ("torch", "dense", "w4a16", "w8a16", "w8a8"):
+            for m in (1, 32):
+                for n, k in shapes:
+                    if kind != "dense" and kind != "torch" and n > 20000:
+                        continue
+                    try:
+                        r = bench_gemm(kind, m, n, k)
+                    except Exception as e:  # keep going: one broken variant must not hide the others
+                        r = {"op": kind, "m": m, "n": n, "k": k, "error": repr(e)[:200]}
+                    if "gbs" in r:
+                        r["frac_hbm"] = r["gbs"] / hbm
+                        r["frac_tensor"] = r["tflops"] / tf
+                    out.append(r)
+        for m in (256, 4096):
+            for kind in ("torch", "dense"):
+                r = bench_gemm(kind, m, 4096, 4096)
+                r["frac_tensor"] = r["tflops"] / tf
+                out.append(r)
+    for r in out:
+        r["peaks"] = src
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
