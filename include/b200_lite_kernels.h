@@ -48,6 +48,8 @@ extern "C" {
 const char* b2l_last_error(void);
 int b2l_version(void);
 int b2l_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
+/* number of kernels this library has launched in this process (monotonic; bench.py's gpu_launches) */
+int64_t b2l_launch_count(void);
 
 /* skip_rmsnorm(X, residual, weight, eps) -- lite_llama/kernels/skip_rmsnorm.py:192-234.
  * residual (nullable) is updated in place with x + residual (rounded to dtype); y gets
@@ -115,7 +117,7 @@ int b2l_linear(void* y, const void* x, const void* w, const void* bias, int64_t 
 
 /* w4a16_matmul(x, qweight, scales, zeros, *, group_size, bias)
  * -- lite_llama/kernels/quantization/w4a16.py:152-207.  fp16 activations only (w4a16.py:174). */
-int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k);
+int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k, int64_t group_k);
 int64_t b2l_quant_gemm_num_counters(int64_t m, int64_t n);
 int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, const void* scales, const void* zeros,
                      const void* bias, int bias_is_f32, int64_t m, int64_t n, int64_t k, int group_size,

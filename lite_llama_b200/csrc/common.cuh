@@ -45,8 +45,12 @@ void b2l_set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+// every kernel launch of this library goes through B2L_LAUNCH_CHECK: count them (bench.py reports it)
+void b2l_count_launch();
+
 #define B2L_LAUNCH_CHECK()                                                          \
   do {                                                                              \
+    b2l_count_launch();                                                             \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) {                                                        \
       b2l_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -11,6 +11,11 @@ void b2l_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void b2l_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t b2l_launch_count(void) { return (int64_t)g_launches.load(); }
+
 extern "C" const char* b2l_last_error(void) { return g_err; }
 extern "C" int b2l_version(void) { return 100; }
 

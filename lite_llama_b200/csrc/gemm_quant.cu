@@ -38,6 +38,7 @@ struct QuantParams {
   int M, N, K;
   int splits, kb_per_split, num_kb;
   int raw_stages;
+  int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
 };
 
 struct __align__(8) QControl {
@@ -118,6 +119,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   constexpr int kXBytes = BT * kStageKBytes;
   constexpr int kRawWBytes = kBlockW * raw_row_bytes<QK>();
   constexpr int kRawStage = raw_stage_bytes<QK, BT>();
+  // per-row scale (and zero-point) table of this CTA's k-range: [group][128 rows] fp32, filled once with
+  // cp.async by the epilogue threads (each thread only ever touches its own column -> no barrier needed)
+  float* scale_tab = reinterpret_cast<float*>(raw_ring + (size_t)p.raw_stages * kRawStage);
+  float* zero_tab = scale_tab + (size_t)p.max_groups * kBlockW;
   constexpr int kAccCols = QK == Q_INT4 ? 2 * BT : BT;            // per buffer: P (+ xsum)
   constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
 
@@ -233,6 +238,27 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
     for (int j = 0; j < BT; ++j) acc[j] = 0.f;
 
+    // stage this row's scales / zero points for every group of the CTA's k-range (asynchronously:
+    // a per-segment global load would put a DRAM round trip on the drain's critical path)
+    const int g_first = k_begin / seg_len;
+    {
+      const int g_last = (k_begin + steps_total * 16 - 1) / seg_len;
+      if (n_ok) {
+        const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n;
+        const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n : nullptr;
+        for (int g = g_first; g <= g_last; ++g) {
+          const int slot = (g - g_first) * kBlockW + epi_tid;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(scale_tab + slot)),
+                       "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
+          if (QK == Q_INT4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zero_tab + slot)),
+                         "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+
     // enumerate segments exactly like the MMA warp does
     int k_pos = k_begin;
     int seg = 0;
@@ -243,8 +269,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int g = k_pos / seg_len;
       float sc = 0.f, zp = 0.f;
       if (n_ok) {
-        sc = p.scales[(int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g * p.s_stride_k];
-        if (QK == Q_INT4) zp = p.zeros[(int64_t)n * p.s_stride_n + (int64_t)g * p.s_stride_k];
+        sc = scale_tab[(g - g_first) * kBlockW + epi_tid];
+        if (QK == Q_INT4) zp = zero_tab[(g - g_first) * kBlockW + epi_tid];
       }
       const int buf = seg & 1;
       mbar_wait(&ctl->acc_full[buf], (seg >> 1) & 1);
@@ -349,7 +375,15 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K) {
+constexpr int kMaxGroupsCta = 48;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
+
+static inline int groups_touched(int kb_per_split, int seg_len) {
+  // worst case over split offsets: a k-range of kb_per_split*64 elements starting anywhere on a 64 boundary
+  const int span = kb_per_split * 64;
+  return (span + seg_len - 1) / seg_len + 1;
+}
+
+static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int seg_len) {
   // token tile capped at 64: the epilogue keeps the running fp32 accumulator in registers
   SplitPlan pl;
   const int64_t mt = M > 64 ? 64 : M;
@@ -368,9 +402,13 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K) {
     if (splits > 32) splits = 32;
   }
   pl.kb_per_split = (pl.num_kb + splits - 1) / splits;
+  // keep the per-CTA scale table bounded: more (smaller) splits when groups are fine-grained
+  while (pl.kb_per_split > 1 && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) --pl.kb_per_split;
   pl.splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+  const int max_groups = groups_touched(pl.kb_per_split, seg_len);
   const int raw_stage = (qk == Q_INT4 ? kBlockW * 32 : kBlockW * 64) + pl.bt * kStageKBytes;
-  const int fixed = 1024 + (qk == Q_INT4 ? kABytes : 0) + kOpStages * kABytes + 1024;
+  const int fixed = 1024 + (qk == Q_INT4 ? kABytes : 0) + kOpStages * kABytes + 1024 +
+                    max_groups * kBlockW * 4 * (qk == Q_INT4 ? 2 : 1);
   int stages = (b2l_max_smem_optin() - fixed) / raw_stage;
   if (stages > kMaxRawStages) stages = kMaxRawStages;
   if (stages > pl.kb_per_split + 1) stages = pl.kb_per_split + 1;
@@ -408,8 +446,9 @@ static int launch_q(const CUtensorMap& tw, const CUtensorMap& tx, const QuantPar
 static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const void* x, const void* qweight,
                         int64_t m, int64_t n, int64_t k, int64_t x_row_stride, int64_t w_row_stride_elems,
                         int64_t y_row_stride, void* workspace, int64_t workspace_bytes, void* counters,
-                        int64_t num_counters, CUtensorMap* tw, CUtensorMap* tx, const char* what) {
-  pl = quant_plan(qk, m, n, k);
+                        int64_t num_counters, CUtensorMap* tw, CUtensorMap* tx, const char* what, int seg_len) {
+  pl = quant_plan(qk, m, n, k, seg_len);
+  p.max_groups = groups_touched(pl.kb_per_split, seg_len);
   p.y = y; p.ldy = y_row_stride; p.M = (int)m; p.N = (int)n; p.K = (int)k;
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.num_kb = pl.num_kb; p.raw_stages = pl.stages;
   p.ws = (uint32_t*)workspace; p.counters = (int*)counters;
@@ -435,9 +474,16 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
 
 using namespace gemm;
 
-extern "C" int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k) {
-  if (m <= 0 || n <= 0 || k <= 0) return 0;
-  SplitPlan pl = quant_plan(kind, m, n, k);
+static inline int seg_len_for(int kind, int64_t k, int64_t group_k) {
+  if (kind == Q_INT4) return (int)group_k;
+  int64_t gk = group_k < k ? group_k : k;
+  if (gk % 16 != 0) gk = k;
+  return (int)((gk + 15) / 16 * 16);
+}
+
+extern "C" int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k, int64_t group_k) {
+  if (m <= 0 || n <= 0 || k <= 0 || group_k <= 0) return 0;
+  SplitPlan pl = quant_plan(kind, m, n, k, seg_len_for(kind, k, group_k));
   if (pl.splits <= 1) return 0;
   return (int64_t)pl.n_tiles * pl.m_tiles * pl.splits * pl.bt * kBlockW * 4;
 }
@@ -461,7 +507,7 @@ extern "C" int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, con
   if (m == 0) return B2L_OK;
   QuantParams p; SplitPlan pl; CUtensorMap tw, tx;
   int rc = quant_common(Q_INT4, p, pl, y, x, qweight, m, n, k, x_row_stride, qw_row_stride, y_row_stride, workspace,
-                        workspace_bytes, counters, num_counters, &tw, &tx, "w4a16_matmul");
+                        workspace_bytes, counters, num_counters, &tw, &tx, "w4a16_matmul", group_size);
   if (rc != B2L_OK) return rc;
   p.bias = bias; p.bias_is_f32 = bias_is_f32;
   p.scales = (const float*)scales; p.zeros = (const float*)zeros; p.s_stride_n = s_row_stride; p.s_stride_k = s_col_stride;
@@ -487,7 +533,7 @@ extern "C" int b2l_w8a16_matmul(void* y, const void* x, const void* qweight, int
   QuantParams p; SplitPlan pl; CUtensorMap tw, tx;
   const int qk = weight_is_fp8 ? Q_FP8 : Q_INT8;
   int rc = quant_common(qk, p, pl, y, x, qweight, m, n, k, x_row_stride, qw_row_stride, y_row_stride, workspace,
-                        workspace_bytes, counters, num_counters, &tw, &tx, "w8a16_matmul");
+                        workspace_bytes, counters, num_counters, &tw, &tx, "w8a16_matmul", seg_len_for(qk, k, group_k));
   if (rc != B2L_OK) return rc;
   p.bias = bias; p.bias_is_f32 = bias_is_f32;
   p.scales = (const float*)scales; p.zeros = nullptr; p.s_stride_n = s_row_stride; p.s_stride_k = s_col_stride;

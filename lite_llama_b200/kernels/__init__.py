@@ -8,7 +8,7 @@ hand-written sm_100a CUDA from ``libb200lite.so`` on the current CUDA stream.
 from .flashattention2_nopad import flash_attention2_no_pad
 from .flashdecoding import flash_decoding
 from .linear import linear
-from .rope_emb import rope_emb_forward
+from .rope_emb import rope_emb_forward, rope_emb_inplace
 from .skip_rmsnorm import skip_rmsnorm
 from .swiglu import swiglu_forward
 from .update_kv_buffer import update_kv_buffer, update_kv_buffer_split
@@ -20,6 +20,7 @@ __all__ = [
     "flash_decoding",
     "linear",
     "rope_emb_forward",
+    "rope_emb_inplace",
     "skip_rmsnorm",
     "swiglu_forward",
     "update_kv_buffer",

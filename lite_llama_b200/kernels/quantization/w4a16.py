@@ -54,7 +54,7 @@ def w4a16_matmul(
             bias_f32 = 1
         bias = bias.contiguous()
     L = lib()
-    nbytes = L.b2l_quant_gemm_workspace_bytes(_Q_INT4, m, n, k)
+    nbytes = L.b2l_quant_gemm_workspace_bytes(_Q_INT4, m, n, k, int(group_size))
     ws = workspace(nbytes, x.device)
     cnt = counters(x.device)
     check(

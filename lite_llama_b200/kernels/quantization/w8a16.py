@@ -54,7 +54,7 @@ def w8a16_matmul(
         bias = bias.contiguous()
     L = lib()
     kind = _Q_FP8 if is_fp8 else _Q_INT8
-    nbytes = L.b2l_quant_gemm_workspace_bytes(kind, m, n, k)
+    nbytes = L.b2l_quant_gemm_workspace_bytes(kind, m, n, k, int(group_k))
     ws = workspace(nbytes, x.device)
     cnt = counters(x.device)
     check(

@@ -33,3 +33,26 @@ def rope_emb_forward(q, k, cos, sin, batch_size, seq_len):
         )
     )
     return q, k
+
+
+@torch.no_grad()
+def rope_emb_inplace(q, k, cos, sin, batch_size, seq_len):
+    """Stride-aware variant used by the host layer: rotates ``q``/``k`` where they lie (e.g. the q and
+    k column blocks of one fused QKV projection output), so no ``.contiguous()`` copy of ``k`` is made
+    (the copy the reference pays at rope_emb.py:107). Only the head_dim axis must be contiguous."""
+    require_cuda(q, k, cos, sin)
+    n, n_qh, hd = q.shape
+    _, n_kh, _ = k.shape
+    assert batch_size * seq_len == n
+    if q.stride(2) != 1 or k.stride(2) != 1 or cos.stride(-1) != 1 or sin.stride(-1) != 1:
+        raise ValueError("rope_emb_inplace: innermost dimension must be contiguous")
+    if cos.dtype != q.dtype or sin.dtype != q.dtype:
+        raise ValueError("rope_emb_inplace: cos/sin must already be in the activation dtype")
+    check(
+        lib().b2l_rope_emb(
+            q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(), batch_size, seq_len, n_qh, n_kh, hd,
+            q.stride(0), q.stride(1), k.stride(0), k.stride(1), cos.stride(0), cos.stride(1),
+            dtype_code(q, "q"), stream_handle(),
+        )
+    )
+    return q, k

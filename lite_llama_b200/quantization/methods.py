@@ -1,0 +1,71 @@
+"""Per-format linear "methods": how a projection's weight is stored and which GEMM applies it.
+
+Mirrors the reference's strategy registry (lite_llama/models/quantization/methods/__init__.py:21-63):
+``fp16`` -> dense GEMM (unquantized.py:21-22), ``int4`` -> w4a16 (w4a16.py:15-43), ``int8`` / ``fp8``
+-> w8a16 (w8a16.py:37-112), ``smoothquant`` -> w8a8 (w8a8.py:15-37).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from ..kernels import linear, smoothquant_matmul, w4a16_matmul, w8a16_matmul
+from .params import quantize_fp8_per_channel, quantize_int4_groupwise, quantize_int8_per_channel
+
+LINEAR_METHODS = ("fp16", "int4", "int8", "fp8", "smoothquant")
+
+
+@dataclass
+class LinearWeights:
+    """Storage of one ``[N, K]`` projection in one of the supported formats."""
+
+    method: str
+    out_features: int
+    in_features: int
+    weight: torch.Tensor | None = None      # fp16/bf16 [N, K]
+    qweight: torch.Tensor | None = None     # int32 [N, K/8] | uint8/int8 [N, K]
+    scales: torch.Tensor | None = None
+    zeros: torch.Tensor | None = None
+    bias: torch.Tensor | None = None
+    group_size: int = 128
+
+    def nbytes(self) -> int:
+        total = 0
+        for t in (self.weight, self.qweight, self.scales, self.zeros, self.bias):
+            if t is not None:
+                total += t.numel() * t.element_size()
+        return total
+
+
+def make_linear_weights(weight: torch.Tensor, method: str, bias: torch.Tensor | None = None,
+                        group_size: int = 128) -> LinearWeights:
+    """Convert a float ``[N, K]`` weight into ``method``'s storage (the ``--quantization`` path of the
+    reference: methods/w4a16.py:39-43, w8a16.py:95-112, w8a8.py:30-37)."""
+    n, k = weight.shape
+    if method == "fp16":
+        return LinearWeights(method, n, k, weight=weight.contiguous(), bias=bias)
+    if method == "int4":
+        q, s, z = quantize_int4_groupwise(weight, group_size)
+        return LinearWeights(method, n, k, qweight=q, scales=s, zeros=z, bias=bias, group_size=group_size)
+    if method in ("int8", "smoothquant"):
+        q, s = quantize_int8_per_channel(weight)
+        return LinearWeights(method, n, k, qweight=q, scales=s, bias=bias)
+    if method == "fp8":
+        q, s = quantize_fp8_per_channel(weight)
+        return LinearWeights(method, n, k, qweight=q, scales=s, bias=bias)
+    raise ValueError(f"unknown linear method {method!r}; expected one of {LINEAR_METHODS}")
+
+
+def apply_linear(x: torch.Tensor, w: LinearWeights) -> torch.Tensor:
+    """``x @ W.T (+ bias)`` through the GEMM that matches ``w.method``."""
+    if w.method == "fp16":
+        return linear(x, w.weight, w.bias)
+    if w.method == "int4":
+        return w4a16_matmul(x, w.qweight, w.scales, w.zeros, group_size=w.group_size, bias=w.bias)
+    if w.method in ("int8", "fp8"):
+        return w8a16_matmul(x, w.qweight, w.scales, group_n=1, group_k=w.in_features, bias=w.bias)
+    if w.method == "smoothquant":
+        return smoothquant_matmul(x, w.qweight, w.scales, bias=w.bias)
+    raise ValueError(f"unknown linear method {w.method!r}")

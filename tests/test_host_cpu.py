@@ -1,0 +1,109 @@
+"""Host-side logic that needs no GPU: KV row allocator, padded-rectangle token table, the quantisers
+against the reference's packers (golden), the TP shard arithmetic and a world_size-2 gloo all-reduce."""
+
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+from b2l_testutil import ROOT, load_golden
+from lite_llama_b200.executor.kv_cache_manager import KVCacheManager
+from lite_llama_b200.executor.model_config import PRESETS
+from lite_llama_b200.quantization import params
+
+
+def test_kv_manager_bump_allocator_and_claim():
+    m = KVCacheManager(num_layers=2, num_kv_heads=2, head_dim=8, gpu_num_blocks=32, device="cpu")
+    assert len(m.gpu_kv_buffer) == 2 and m.gpu_kv_buffer[0].shape == (32, 4, 8)
+    a = m.alloc_kvcache_index(10)
+    b = m.alloc_kvcache_index(4)
+    assert a.dtype == torch.int32 and a.tolist() == list(range(10)) and b.tolist() == [10, 11, 12, 13]
+    assert m.can_use_mem_size == 18
+    assert m.alloc_kvcache_index(19) is None          # short: the reference also returns None
+    m.free_all()
+    assert m.alloc_kvcache_index(3).tolist() == [0, 1, 2]
+    m.free_all()
+    m.claim(16)
+    assert m.alloc_kvcache_index(2).tolist() == [16, 17]
+    with pytest.raises(ValueError):
+        m.claim(100)
+
+
+def test_prefill_table_uses_the_padded_rectangle_layout():
+    # sequence i's j-th token is flattened row i*max_prompt_len + j (model_runner.py:153-179 in the reference)
+    from lite_llama_b200.executor.model_runner import ModelRunner
+
+    r = ModelRunner.__new__(ModelRunner)
+    r.device = "cpu"
+    r.b_req_tokens_table = torch.zeros(4, 16, dtype=torch.int32)
+    alloc = torch.arange(100, 100 + 3 * 5, dtype=torch.int32)
+    start = ModelRunner._init_req_tokens_table(r, torch.tensor([2, 0, 3]), torch.tensor([5, 2, 4]), alloc, 5)
+    assert start.tolist() == [0, 5, 10]
+    assert r.b_req_tokens_table[2, :5].tolist() == [100, 101, 102, 103, 104]
+    assert r.b_req_tokens_table[0, :3].tolist() == [105, 106, 0]
+    assert r.b_req_tokens_table[3, :5].tolist() == [110, 111, 112, 113, 0]
+    assert r.b_req_tokens_table[1].abs().sum() == 0
+
+
+def test_int4_packer_is_bit_identical_to_the_reference_packer():
+    for c in load_golden("w4a16")["cases"]:
+        q, s, z = params.quantize_int4_groupwise(c["w"], c["group_size"])
+        assert torch.equal(q, c["qweight"]) and torch.equal(s, c["scales"]) and torch.equal(z, c["zeros"])
+
+
+def test_int8_and_fp8_packers_match_the_reference_packers():
+    for c in load_golden("w8a16")["cases"]:
+        q, s = params.quantize_int8_per_channel(c["w"])
+        assert torch.equal(q, c["int8_channel"]["qweight"]) and torch.equal(s, c["int8_channel"]["scales"])
+        q, s = params.quantize_fp8_per_channel(c["w"])
+        assert torch.equal(q, c["fp8_channel"]["qweight"]) and torch.equal(s, c["fp8_channel"]["scales"])
+
+
+def test_presets_have_the_public_geometries():
+    l3 = PRESETS["llama-3-8b"]
+    assert (l3.hidden_size, l3.num_layers, l3.num_heads, l3.num_kv_heads, l3.head_dim, l3.intermediate_size,
+            l3.vocab_size) == (4096, 32, 32, 8, 128, 14336, 128256)
+    q7 = PRESETS["qwen2.5-7b"]
+    assert (q7.hidden_size, q7.num_heads, q7.num_kv_heads, q7.intermediate_size, q7.qkv_bias) == (3584, 28, 4, 18944, True)
+    for cfg in PRESETS.values():
+        cfg.validate()
+
+
+_TP_SCRIPT = textwrap.dedent("""
+    import os, sys, torch
+    sys.path.insert(0, {root!r})
+    from lite_llama_b200.distributed import init_tensor_parallel, all_reduce_tp, all_reduce_min, get_tp_rank, get_tp_world_size, divide, destroy_tensor_parallel
+    init_tensor_parallel(backend="gloo")
+    r, w = get_tp_rank(), get_tp_world_size()
+    assert w == 2
+    # row-parallel partial sums: each rank holds x[:, shard] @ W[:, shard].T, the all-reduce restores x @ W.T
+    torch.manual_seed(0)
+    x, W = torch.randn(3, 8), torch.randn(5, 8)
+    k = divide(8, w, "K")
+    part = x[:, r*k:(r+1)*k] @ W[:, r*k:(r+1)*k].T
+    full = all_reduce_tp(part.clone())
+    torch.testing.assert_close(full, x @ W.T, rtol=1e-5, atol=1e-5)
+    assert all_reduce_min(100 - 10 * r) == 90
+    try:
+        divide(7, 2, "heads"); raise SystemExit("divide must reject 7/2")
+    except ValueError:
+        pass
+    destroy_tensor_parallel()
+    print("rank", r, "ok")
+""")
+
+
+def test_tensor_parallel_all_reduce_world_size_2_gloo(tmp_path):
+    script = tmp_path / "tp2.py"
+    script.write_text(_TP_SCRIPT.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -1,0 +1,151 @@
+"""End-to-end parity of the host layer (lite_llama_b200.executor) on tiny geometries: the GPU forward
+(prefill over the padded rectangle, eager decode, captured decode graph, the fully captured greedy
+loop) against the CPU restatement of the reference forward (oracle/model.py), with identical weights.
+
+Logit tolerance: fp16 activations through 2 layers; rtol 2e-2 / atol 2e-2 on logits of O(0.3), the
+same bar the reference uses for whole-model parity (tests/models/test_qwen3_moe.py:185-245 uses
+cosine > 0.985). Greedy tokens are additionally required to be identical wherever the oracle's
+top-2 margin is decidable (> 4x the logit tolerance)."""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+from oracle import model as omodel
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def _build(name, quant, max_seq_len=64, batch=3):
+    from lite_llama_b200.executor import PRESETS, ModelRunner
+
+    cfg = PRESETS[name]
+    runner = ModelRunner.build(name, max_seq_len=max_seq_len, max_gpu_num_blocks=batch * max_seq_len, device="cuda",
+                               quantization=quant, seed=0, draw_device="cpu")
+    embed, lm_head, layers = omodel.random_cpu_layers(cfg, quant or "fp16", cfg.num_layers, seed=0)
+    cpu = omodel.CpuDecoder(cfg, embed, lm_head, layers, max_tokens=batch * max_seq_len, max_pos=max_seq_len,
+                            method=quant or "fp16")
+    return cfg, runner, cpu
+
+
+def _check_logits(got, ref, tol=2e-2):
+    got, ref = got.float().cpu(), ref.float()
+    torch.testing.assert_close(got, ref, rtol=tol, atol=tol)
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
+    assert cos > 0.999, f"cosine {cos}"
+
+
+def _decidable_equal(got_logits, ref_logits, margin=8e-2):
+    ref = ref_logits.float()
+    top2 = ref.topk(2, dim=-1).values
+    decidable = (top2[..., 0] - top2[..., 1]) > margin
+    same = got_logits.float().cpu().argmax(-1) == ref.argmax(-1)
+    assert bool((same | ~decidable).all()), "greedy token differs where the oracle's argmax is decidable"
+
+
+@pytest.mark.parametrize("name,quant", [("tiny-llama", None), ("tiny-llama", "int4"), ("tiny-qwen2", "int8"),
+                                        ("tiny-qwen2", "fp8"), ("tiny-qwen3", "smoothquant"), ("tiny-qwen3", None)])
+def test_prefill_then_decode_matches_the_cpu_restatement(name, quant):
+    cfg, runner, cpu = _build(name, quant)
+    B, P = 3, 12
+    lens = torch.tensor([12, 7, 9])
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, cfg.vocab_size, (B, P), generator=g)
+    pos = torch.arange(P).repeat(B, 1)
+    b_req = torch.arange(B)
+    # GPU: padded rectangle prefill
+    sel = runner.prefill_alloc_kv_cache(P, lens.cuda(), b_req.cuda())
+    logits = runner.forward(ids.cuda(), pos.cuda())
+    # CPU restatement with the same rows / table
+    table = runner.b_req_tokens_table.cpu().clone()
+    start = (torch.arange(B) * P).to(torch.int32)
+    ref = cpu.forward(ids, pos, sel.cpu(), table, b_req, lens, start)
+    for i in range(B):   # padding positions are don't-care (reference leaves them uninitialised)
+        _check_logits(logits[i, : lens[i]], ref[i, : lens[i]])
+    last = lens - 1
+    tok = logits[torch.arange(B), last.cuda()].argmax(-1)
+    _decidable_equal(logits[torch.arange(B), last.cuda()], ref[torch.arange(B), last])
+    # three eager decode steps
+    cur_lens = lens.clone()
+    tok_cpu = ref[torch.arange(B), last].argmax(-1)
+    for _ in range(3):
+        sel = runner.decode_alloc_kv_cache(B)
+        cur_lens += 1
+        p1 = (cur_lens - 1).view(B, 1)
+        out = runner.forward(tok_cpu.view(B, 1).cuda(), p1.cuda())
+        table = runner.b_req_tokens_table.cpu().clone()
+        ref1 = cpu.forward(tok_cpu.view(B, 1), p1, sel.cpu(), table, b_req, cur_lens)
+        _check_logits(out, ref1)
+        _decidable_equal(out[:, -1], ref1[:, -1])
+        tok_cpu = ref1[:, -1].argmax(-1)   # teacher-force the oracle's token so both sides see one history
+
+
+def test_captured_decode_graph_equals_eager():
+    cfg, runner, _ = _build("tiny-llama", "int4", max_seq_len=256, batch=4)
+    from lite_llama_b200.executor import ModelRunner
+
+    B, P = 4, 20
+    lens = torch.tensor([20, 3, 11, 16]).cuda()
+    ids = torch.randint(0, cfg.vocab_size, (B, P)).cuda()
+    pos = torch.arange(P).repeat(B, 1).cuda()
+    b_req = torch.arange(B).cuda()
+
+    def run(graph: bool):
+        runner.kv_cache_manager.free_all()
+        runner.prefill_alloc_kv_cache(P, lens.clone(), b_req)
+        logits = runner.forward(ids, pos, last_token_index=lens - 1)
+        tok = logits[:, -1].argmax(-1)
+        toks = [tok]
+        p = lens.clone().view(B, 1)
+        for _ in range(6):
+            runner.decode_alloc_kv_cache(B)
+            if graph:
+                out = runner.forward(tok.view(B, 1), p)
+            else:
+                out = runner.model.forward(tok.view(B, 1), p, runner.atten_info)
+            tok = out[:, -1].argmax(-1)
+            toks.append(tok)
+            p = p + 1
+        return torch.stack(toks).cpu()
+
+    eager = run(False)
+    runner.enable_cuda_graph(batch_sizes=(4,), seq_len_buckets=(256,))
+    assert runner.graph_batch_size(3) == 4
+    graphed = run(True)
+    assert torch.equal(eager, graphed), "graph replay must be byte-identical to eager (reference: tests/compile/test_cuda_graph.py)"
+
+
+def test_greedy_decode_loop_matches_step_by_step_api():
+    cfg, runner, _ = _build("tiny-llama", None, max_seq_len=256, batch=4)
+    from lite_llama_b200.executor.model_runner import GreedyDecodeLoop
+
+    B, P, steps = 4, 9, 7
+    lens = torch.full((B,), P).cuda()
+    ids = torch.randint(0, cfg.vocab_size, (B, P)).cuda()
+    pos = torch.arange(P).repeat(B, 1).cuda()
+    b_req = torch.arange(B).cuda()
+
+    def prefill():
+        runner.kv_cache_manager.free_all()
+        runner.prefill_alloc_kv_cache(P, lens.clone(), b_req)
+        return runner.forward(ids, pos, last_token_index=lens - 1)[:, -1].argmax(-1)
+
+    tok = prefill()
+    expect = []
+    p = lens.clone().view(B, 1)
+    for _ in range(steps):
+        runner.decode_alloc_kv_cache(B)
+        tok = runner.forward(tok.view(B, 1), p)[:, -1].argmax(-1)
+        expect.append(tok.cpu())
+        p = p + 1
+    first = prefill()
+    loop = GreedyDecodeLoop(runner, B, 256)
+    loop.begin(first, lens, b_req, runner.kv_cache_manager._bump_cursor)
+    loop.capture()
+    got = []
+    for _ in range(steps):
+        loop.step()
+        got.append(loop.next_tokens.cpu().clone())
+    assert torch.equal(torch.stack(got), torch.stack(expect))
+    assert loop.launches_per_step > 0

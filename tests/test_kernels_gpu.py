@@ -471,19 +471,24 @@ def test_w8a16_matches_oracle(m, n, k):
 def test_fp8_dequant_is_exact_for_every_code():
     # each finite e4m3 code, read back through a one-hot activation, must equal its exact value
     codes = torch.arange(256, dtype=torch.int32).to(torch.uint8)
-    qw = codes.repeat(128, 1)[:, :256].contiguous()              # [128, 256]
+    finite = (codes & 0x7F) != 0x7F
+    safe = torch.where(finite, codes, torch.zeros_like(codes))   # NaN codes would poison every dot product
+    qw = safe.repeat(128, 1).contiguous()                        # [128, 256]
     x = torch.eye(256, dtype=torch.float16, device="cuda")
     out = K().w8a16_matmul(x, qw.cuda(), torch.ones(1, 1, device="cuda"), group_n=128, group_k=256)
-    finite = (codes & 0x7F) != 0x7F
     expect = codes.view(torch.float8_e4m3fn).float()
     assert torch.equal(out.cpu()[:, 0].float()[finite], expect[finite])
+    assert torch.equal(out.cpu()[:, 77].float()[finite], expect[finite])
 
 
 def test_smoothquant_golden_and_quantiser_codes():
     for c in load_golden("w8a8")["cases"]:
         g = to_cuda(c)
         out = K().smoothquant_matmul(g["x"], g["qweight"], g["weight_scales"], bias=g["bias"])
-        close(out, c["out"], rtol=2e-3, atol=1e-3)
+        # the golden was recorded with IEEE division (Triton interpreter); the GPU path (ours and the
+        # reference's) divides with div.full.f32, so an activation code may differ by one count at a
+        # truncation boundary: |delta| <= max|w_dequant| * a_scale ~ 3e-3 here
+        close(out, c["out"], rtol=2e-3, atol=4e-3)
     from lite_llama_b200.kernels.quantization.w8a8 import quantize_activations_int8
 
     x = torch.randn(64, 2048, device="cuda", dtype=torch.float16) * 0.5

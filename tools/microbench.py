@@ -40,9 +40,21 @@ def flush_l2():
 
 
 def timeit(fn, iters=20, warmup=3, flush=True):
+    """Median device time of ``fn`` replayed from a CUDA graph (no Python/launch overhead inside the
+    timed region), L2 flushed before every replay."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        fn()
+    fn = graph.replay
     ts = []
     for _ in range(iters):
         if flush:
