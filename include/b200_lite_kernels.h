@@ -142,8 +142,30 @@ int b2l_w8a8_gemm(void* y, const void* xq, const void* wq, const void* a_scale, 
                   int64_t wq_row_stride, int64_t y_row_stride, void* workspace, int64_t workspace_bytes,
                   void* counters, int64_t num_counters, int out_dtype, void* stream);
 
-/* fused_moe pieces -- lite_llama/kernels/fused_moe.py:45-99 (align), :316-333 (sum). */
+/* fused_moe(hidden_states, w1, w2, topk_weights, topk_ids, *, w1_scale, w2_scale, group_n, group_k)
+ * -- lite_llama/kernels/fused_moe.py:352-438 -- is moe_align_block_size (:45-99), grouped GEMM1
+ * (b2l_moe_gemm), silu_and_mul (b2l_swiglu on the two halves, :296-313), grouped GEMM2 with the routing
+ * weight folded in (b2l_moe_gemm, :201-205) and moe_sum (:316-333).
+ *
+ * moe_align_block_size(topk_ids, block_size, num_experts): sorted_token_ids int32
+ * [num_slots + E*(block-1)] (sentinel = num_slots), expert_ids int32 [ceil(that / block)],
+ * num_tokens_post_padded int32 [1]; topk_ids int32 or int64. */
+int b2l_moe_align_block_size(const void* topk_ids, int id_width, int64_t num_slots, int block_size, int num_experts,
+                             void* sorted_token_ids, void* expert_ids, void* num_tokens_post_padded, void* stream);
+/* C[slot, :] = A[slot / top_k, :] @ W[expert(block)].T (* topk_weights[slot] when non-null).  fp16 activations.
+ * weight_kind: 0 = fp16 [E, N, K], B2L_Q_FP8 / B2L_Q_INT8 = 8-bit with fp32 scales
+ * [E, ceil(N/group_n), ceil(K/group_k)] (element strides s_stride_*).  block_size in {16, 32, 64}. */
+int b2l_moe_gemm(void* c, const void* a, const void* w, int weight_kind, const void* scales,
+                 const void* topk_weights, const void* sorted_token_ids, const void* expert_ids,
+                 const void* num_tokens_post_padded, int64_t em, int64_t num_valid_slots, int top_k, int block_size,
+                 int num_experts, int64_t n, int64_t k, int64_t a_row_stride, int64_t w_row_stride,
+                 int64_t c_row_stride, int64_t group_n, int64_t group_k, int64_t s_stride_e, int64_t s_stride_n,
+                 int64_t s_stride_k, void* stream);
 int b2l_moe_sum(void* out, const void* in, int64_t tokens, int64_t n, int top_k, int dtype, void* stream);
+/* Router (lite_llama/models/qwen3_moe.py:94-100): fp32 softmax over all experts of the [tokens, E] logits,
+ * top-k (ties -> lowest index), optional renormalisation; weights in the activation dtype, ids int64. */
+int b2l_moe_route_topk(void* topk_weights, void* topk_ids_i64, const void* router_logits, int64_t row_stride,
+                       int64_t tokens, int num_experts, int top_k, int renormalize, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

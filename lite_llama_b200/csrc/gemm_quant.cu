@@ -23,8 +23,8 @@ namespace gemm {
 
 constexpr int kDequantWarps = 8;
 constexpr int kQuantThreads = (2 + 4 + kDequantWarps) * 32;   // 448
-constexpr int kOpStages = 4;                                  // dequantised-operand ring depth
-constexpr int kMaxRawStages = 16;
+constexpr int kOpStages = 3;                                  // dequantised-operand ring depth
+constexpr int kMaxRawStages = 8;
 
 enum QuantKind { Q_INT4 = 0, Q_FP8 = 1, Q_INT8 = 2 };
 
@@ -53,9 +53,12 @@ struct __align__(8) QControl {
 };
 static_assert(sizeof(QControl) <= 1024, "control block too large");
 
-template <int QK> __host__ __device__ constexpr int raw_row_bytes() { return QK == Q_INT4 ? 32 : 64; }
+// A raw stage holds 128 weight rows x 128 BYTES of quantised K (TMA needs full 128-byte rows to stream
+// HBM efficiently: with 32/64-byte rows the first version reached 5-10 % of peak) = RW operand k-blocks
+// of 64 elements (int4: 256 elements -> 4, 8-bit: 128 -> 2), plus the RW activation sub-tiles.
+template <int QK> __host__ __device__ constexpr int raw_sub() { return QK == Q_INT4 ? 4 : 2; }
 template <int QK, int BT> __host__ __device__ constexpr int raw_stage_bytes() {
-  return kBlockW * raw_row_bytes<QK>() + BT * kStageKBytes;
+  return kABytes + raw_sub<QK>() * BT * kStageKBytes;
 }
 
 // ---- dequantisers: 8 packed weights -> 8 fp16 values in K order (one 16-byte operand chunk) ----
@@ -116,9 +119,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint8_t* ones_tile = smem + 1024;                               // int4: 128 x 64 fp16 ones (16 KiB)
   uint8_t* op_ring = ones_tile + (QK == Q_INT4 ? kABytes : 0);    // kOpStages x 16 KiB
   uint8_t* raw_ring = op_ring + kOpStages * kABytes;              // raw_stages x (X tile, raw W tile)
-  constexpr int kXBytes = BT * kStageKBytes;
-  constexpr int kRawWBytes = kBlockW * raw_row_bytes<QK>();
-  constexpr int kRawStage = raw_stage_bytes<QK, BT>();
+  constexpr int kXBytes = BT * kStageKBytes;          // one activation sub-tile (64 K elements)
+  constexpr int RW = raw_sub<QK>();
+  constexpr int kRawStage = raw_stage_bytes<QK, BT>(); // [raw W 16 KiB (128B-swizzled)] [RW x X sub-tile]
   // per-row scale (and zero-point) table of this CTA's k-range: [group][128 rows] fp32, filled once with
   // cp.async by the epilogue threads (each thread only ever touches its own column -> no barrier needed)
   float* scale_tab = reinterpret_cast<float*>(raw_ring + (size_t)p.raw_stages * kRawStage);
@@ -174,15 +177,19 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       PipeState rs(p.raw_stages);
-      for (int i = 0; i < nkb; ++i) {
+      const int nrb = (nkb + RW - 1) / RW;
+      for (int rb = 0; rb < nrb; ++rb) {
         mbar_wait(&ctl->raw_empty[rs.stage], rs.phase ^ 1);
-        mbar_arrive_expect_tx(&ctl->raw_full[rs.stage], kRawStage);
+        mbar_arrive_expect_tx(&ctl->raw_full[rs.stage], kRawStage);   // OOB parts are zero-filled but still counted
         uint8_t* st = raw_ring + (size_t)rs.stage * kRawStage;
-        const int kb = kb0 + i;
-        tma_load_2d_hint(st, &tmap_x, kb * 64, m_tile * BT, &ctl->raw_full[rs.stage], kEvictLast);
-        // raw weight tile: int4 -> 8 int32 words per row per stage; 8-bit -> 64 bytes per row
-        tma_load_2d_hint(st + kXBytes, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64, n_tile * kBlockW,
-                         &ctl->raw_full[rs.stage], kEvictFirst);
+        const int kb = kb0 + rb * RW;                                  // first 64-element k-block of this raw block
+        // raw weight tile: 128 rows x 128 bytes (int4: 32 int32 words = 256 K; 8-bit: 128 K), 128B-swizzled
+        tma_load_2d_hint(st, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64, n_tile * kBlockW, &ctl->raw_full[rs.stage],
+                         kEvictFirst);
+#pragma unroll
+        for (int sub = 0; sub < RW; ++sub)
+          tma_load_2d_hint(st + kABytes + sub * kXBytes, &tmap_x, (kb + sub) * 64, m_tile * BT,
+                           &ctl->raw_full[rs.stage], kEvictLast);
         rs.advance();
       }
     }
@@ -196,11 +203,13 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       int in_seg = 0;        // 16-element steps already issued into the open segment
       int step = 0;          // global step index within this CTA's k-range
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&ctl->raw_full[rs.stage], rs.phase);   // activation tile (written by TMA)
+        const int sub = i % RW;
+        if (sub == 0) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);   // activation sub-tiles (written by TMA)
         mbar_wait(&ctl->op_full[os.stage], os.phase);    // dequantised weight tile
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(op_ring + (size_t)os.stage * kABytes));
-        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(raw_ring + (size_t)rs.stage * kRawStage));
+        const uint64_t bdesc = umma_desc_sw128_kmajor(
+            smem_u32(raw_ring + (size_t)rs.stage * kRawStage + kABytes + sub * kXBytes));
 #pragma unroll 1
         for (int k = 0; k < 4 && step < steps_total; ++k, ++step) {
           const int buf = seg & 1;
@@ -221,9 +230,11 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           }
         }
         tc_commit(&ctl->op_empty[os.stage]);
-        tc_commit(&ctl->raw_empty[rs.stage]);
-        rs.advance();
         os.advance();
+        if (sub == RW - 1 || i + 1 == nkb) {
+          tc_commit(&ctl->raw_empty[rs.stage]);
+          rs.advance();
+        }
       }
     }
   } else if (warp < 6) {
@@ -333,15 +344,20 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   } else {
     // ===================== dequant warps (6..13) =====================
     const int dt = threadIdx.x - 6 * 32;          // 0..255
-    const int row = dt >> 1, hsel = dt & 1;
+    // 8 consecutive threads = 8 consecutive rows: their 16-byte accesses hit 8 different swizzled chunks,
+    // so both the raw-tile loads and the operand-tile stores are bank-conflict free
+    const int row = dt & 127, hsel = dt >> 7;
+    const int rx = row & 7;
     PipeState rs(p.raw_stages), os(kOpStages);
     for (int i = 0; i < nkb; ++i) {
-      mbar_wait(&ctl->raw_full[rs.stage], rs.phase);
+      const int sub = i % RW;
+      if (sub == 0) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);
       mbar_wait(&ctl->op_empty[os.stage], os.phase ^ 1);
-      const uint8_t* rawp = raw_ring + (size_t)rs.stage * kRawStage + kXBytes + row * raw_row_bytes<QK>();
+      const uint8_t* rawrow = raw_ring + (size_t)rs.stage * kRawStage + row * 128;
       uint8_t* arow = op_ring + (size_t)os.stage * kABytes + row * 128;
       if (QK == Q_INT4) {
-        const uint4 w4 = *reinterpret_cast<const uint4*>(rawp + hsel * 16);
+        // this k-block's 64 nibbles of the row = logical 16-byte chunks 2*sub, 2*sub+1; this thread takes one
+        const uint4 w4 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2 + hsel) ^ rx) << 4));
         const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -349,8 +365,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           *reinterpret_cast<uint4*>(arow + ((chunk ^ (row & 7)) << 4)) = dequant_int4_word(ws[j]);
         }
       } else {
-        const uint4 lo4 = *reinterpret_cast<const uint4*>(rawp + hsel * 32);
-        const uint4 hi4 = *reinterpret_cast<const uint4*>(rawp + hsel * 32 + 16);
+        // this k-block's 64 bytes of the row = logical chunks 4*sub .. 4*sub+3; this thread takes two
+        const int c0 = sub * 4 + hsel * 2;
+        const uint4 lo4 = *reinterpret_cast<const uint4*>(rawrow + ((c0 ^ rx) << 4));
+        const uint4 hi4 = *reinterpret_cast<const uint4*>(rawrow + (((c0 + 1) ^ rx) << 4));
         const uint32_t ws[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -361,12 +379,13 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
+      const bool raw_done = (sub == RW - 1) || (i + 1 == nkb);
       if (lane == 0) {
         mbar_arrive(&ctl->op_full[os.stage]);
-        mbar_arrive(&ctl->raw_empty[rs.stage]);
+        if (raw_done) mbar_arrive(&ctl->raw_empty[rs.stage]);
       }
-      rs.advance();
       os.advance();
+      if (raw_done) rs.advance();
     }
   }
 
@@ -375,7 +394,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-constexpr int kMaxGroupsCta = 48;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
+constexpr int kMaxGroupsCta = 24;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
 
 static inline int groups_touched(int kb_per_split, int seg_len) {
   // worst case over split offsets: a k-range of kb_per_split*64 elements starting anywhere on a 64 boundary
@@ -401,17 +420,18 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
     if (splits > max_splits) splits = max_splits;
     if (splits > 32) splits = 32;
   }
-  pl.kb_per_split = (pl.num_kb + splits - 1) / splits;
+  const int rw = qk == Q_INT4 ? 4 : 2;     // k-blocks per raw stage: splits must start on a raw-block boundary
+  pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
   // keep the per-CTA scale table bounded: more (smaller) splits when groups are fine-grained
-  while (pl.kb_per_split > 1 && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) --pl.kb_per_split;
+  while (pl.kb_per_split > rw && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) pl.kb_per_split -= rw;
   pl.splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;
   const int max_groups = groups_touched(pl.kb_per_split, seg_len);
-  const int raw_stage = (qk == Q_INT4 ? kBlockW * 32 : kBlockW * 64) + pl.bt * kStageKBytes;
+  const int raw_stage = kABytes + rw * pl.bt * kStageKBytes;
   const int fixed = 1024 + (qk == Q_INT4 ? kABytes : 0) + kOpStages * kABytes + 1024 +
                     max_groups * kBlockW * 4 * (qk == Q_INT4 ? 2 : 1);
   int stages = (b2l_max_smem_optin() - fixed) / raw_stage;
   if (stages > kMaxRawStages) stages = kMaxRawStages;
-  if (stages > pl.kb_per_split + 1) stages = pl.kb_per_split + 1;
+  if (stages > pl.kb_per_split / rw + 1) stages = pl.kb_per_split / rw + 1;
   if (stages < 2) stages = 2;
   pl.stages = stages;
   pl.smem_bytes = fixed + stages * raw_stage;
@@ -461,10 +481,10 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   int rc;
   if (qk == Q_INT4)
     rc = b2l_make_tmap_2d(tw, qweight, TMA_I32, (uint64_t)n, (uint64_t)(k / 8), (uint64_t)w_row_stride_elems * 4,
-                          kBlockW, 8, false);
+                          kBlockW, 32, true);
   else
-    rc = b2l_make_tmap_2d(tw, qweight, TMA_U8, (uint64_t)n, (uint64_t)k, (uint64_t)w_row_stride_elems, kBlockW, 64,
-                          false);
+    rc = b2l_make_tmap_2d(tw, qweight, TMA_U8, (uint64_t)n, (uint64_t)k, (uint64_t)w_row_stride_elems, kBlockW, 128,
+                          true);
   if (rc != B2L_OK) return rc;
   return b2l_make_tmap_2d(tx, x, TMA_F16, (uint64_t)m, (uint64_t)k, (uint64_t)x_row_stride * 2, (uint32_t)pl.bt, 64,
                           true);

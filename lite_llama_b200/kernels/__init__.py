@@ -7,6 +7,7 @@ hand-written sm_100a CUDA from ``libb200lite.so`` on the current CUDA stream.
 
 from .flashattention2_nopad import flash_attention2_no_pad
 from .flashdecoding import flash_decoding
+from .fused_moe import fused_moe, moe_align_block_size, route_topk
 from .linear import linear
 from .rope_emb import rope_emb_forward, rope_emb_inplace
 from .skip_rmsnorm import skip_rmsnorm
@@ -18,6 +19,9 @@ from .quantization import smoothquant_matmul, w4a16_matmul, w8a16_matmul
 __all__ = [
     "flash_attention2_no_pad",
     "flash_decoding",
+    "fused_moe",
+    "moe_align_block_size",
+    "route_topk",
     "linear",
     "rope_emb_forward",
     "rope_emb_inplace",

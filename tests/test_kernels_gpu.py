@@ -515,3 +515,95 @@ def test_smoothquant_matches_oracle(m, n, k):
     ref = (acc.float() * sa.cpu().unsqueeze(-1) * scale.unsqueeze(0)).half()
     close(out, ref, rtol=1e-3, atol=5e-4)
     close(out, ops.smoothquant_matmul(x.cpu(), qw, scale), rtol=2e-2, atol=2e-2)
+
+
+# --------------------------------------------------------------------------- #
+# MoE: align (bit-exact), router, grouped GEMMs
+# --------------------------------------------------------------------------- #
+def test_moe_align_golden_bit_exact():
+    for c in load_golden("moe_align")["cases"]:
+        s, e, n = K().moe_align_block_size(c["topk_ids"].cuda(), c["block_size"], c["num_experts"])
+        assert torch.equal(s.cpu(), c["sorted_ids"]) and torch.equal(e.cpu(), c["expert_ids"]) and torch.equal(n.cpu(), c["num_post"])
+
+
+@pytest.mark.parametrize("tokens,experts,top_k,block", [(1, 8, 2, 16), (37, 128, 8, 32), (513, 128, 8, 64), (4096, 60, 4, 64),
+                                                        (3, 1, 1, 16)])
+@pytest.mark.parametrize("dt", [torch.int32, torch.int64])
+def test_moe_align_matches_oracle_bit_exact(tokens, experts, top_k, block, dt):
+    ids = torch.randint(0, experts, (tokens, top_k), dtype=dt)
+    s, e, n = K().moe_align_block_size(ids.cuda(), block, experts)
+    s_ref, e_ref, n_ref = ops.moe_align_block_size(ids, block, experts)
+    assert torch.equal(n.cpu(), n_ref) and torch.equal(s.cpu(), s_ref) and torch.equal(e.cpu(), e_ref)
+
+
+@pytest.mark.parametrize("tokens,experts,top_k", [(1, 128, 8), (37, 128, 8), (5, 8, 2), (64, 60, 4), (3, 512, 8)])
+def test_moe_route_topk_matches_oracle(tokens, experts, top_k):
+    logits = (torch.randn(tokens, experts) * 2).half()
+    w, ids = K().route_topk(logits.cuda(), top_k, True)
+    probs = torch.softmax(logits.float(), dim=-1)
+    w_ref, ids_ref = torch.topk(probs, top_k, dim=-1)
+    w_ref = (w_ref / w_ref.sum(-1, keepdim=True)).half()
+    # ids must agree wherever the k-th and (k+1)-th probabilities are distinguishable
+    srt = probs.sort(dim=-1, descending=True).values
+    decidable = ((srt[:, :top_k] - srt[:, 1 : top_k + 1]) > 1e-6).all(dim=-1) if experts > top_k else torch.ones(tokens, dtype=torch.bool)
+    assert torch.equal(ids.cpu()[decidable], ids_ref[decidable])
+    close(w.cpu()[decidable], w_ref[decidable], rtol=2e-3, atol=1e-4)
+
+
+def test_fused_moe_golden():
+    for c in load_golden("fused_moe")["cases"]:
+        g = to_cuda(c)
+        out = K().fused_moe(g["hidden"], g["w1"], g["w2"], g["topk_weights"], g["topk_ids"],
+                            w1_scale=g.get("w1_scale"), w2_scale=g.get("w2_scale"),
+                            group_n=c.get("group_n", 0), group_k=c.get("group_k", 0))
+        close(out, c["out"], rtol=5e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("num_tokens", [1, 3, 37, 128])
+@pytest.mark.parametrize("num_experts,top_k", [(8, 2), (128, 8)])
+def test_fused_moe_matches_oracle(num_tokens, num_experts, top_k):
+    hidden, inter = 256, 128
+    x = (torch.randn(num_tokens, hidden) / hidden**0.5).half()
+    w1 = (torch.randn(num_experts, 2 * inter, hidden) / hidden**0.5).half()
+    w2 = (torch.randn(num_experts, hidden, inter) / inter**0.5).half()
+    ids = torch.randint(0, num_experts, (num_tokens, top_k))
+    tw = torch.softmax(torch.randn(num_tokens, top_k), dim=-1).half()
+    out = K().fused_moe(x.cuda(), w1.cuda(), w2.cuda(), tw.cuda(), ids.cuda())
+    ref = ops.fused_moe(x, w1, w2, tw, ids)
+    close(out, ref, rtol=5e-3, atol=5e-4)
+
+
+@pytest.mark.parametrize("kind", ["fp8", "int8"])
+def test_fused_moe_quantised_experts_qwen3_shape(kind):
+    # Qwen3-30B-A3B slice: hidden 2048, moe_intermediate 768, 128x128 fp8 blocks (config 5), fewer experts
+    tokens, E, top_k, hidden, inter = 32, 16, 4, 2048, 768
+    x = (torch.randn(tokens, hidden) / hidden**0.5).half()
+    w1f = torch.randn(E, 2 * inter, hidden) / hidden**0.5
+    w2f = torch.randn(E, hidden, inter) / inter**0.5
+    if kind == "fp8":
+        w1, w2 = w1f.to(torch.float8_e4m3fn).view(torch.uint8), w2f.to(torch.float8_e4m3fn).view(torch.uint8)
+        s1 = torch.rand(E, 2 * inter // 128, hidden // 128) + 0.5
+        s2 = torch.rand(E, hidden // 128, inter // 128) + 0.5
+        gn = gk = 128
+    else:
+        w1, s1 = ops.quantize_int8_per_channel(w1f)
+        w2, s2 = ops.quantize_int8_per_channel(w2f)
+        gn, gk = 1, 1 << 30
+    ids = torch.randint(0, E, (tokens, top_k))
+    tw = torch.softmax(torch.randn(tokens, top_k), dim=-1).half()
+    out = K().fused_moe(x.cuda(), w1.cuda(), w2.cuda(), tw.cuda(), ids.cuda(), w1_scale=s1.cuda(), w2_scale=s2.cuda(),
+                        group_n=gn, group_k=gk)
+    ref = ops.fused_moe(x, w1, w2, tw, ids, s1, s2, gn, min(gk, 1 << 20))
+    close(out, ref, rtol=5e-3, atol=1e-3)
+
+
+def test_fused_moe_zero_routing_weight_drops_the_slot():
+    hidden, inter, E, top_k = 128, 64, 4, 2
+    x = torch.randn(5, hidden).half()
+    w1 = (torch.randn(E, 2 * inter, hidden) / hidden**0.5).half()
+    w2 = (torch.randn(E, hidden, inter) / inter**0.5).half()
+    ids = torch.randint(0, E, (5, top_k))
+    tw = torch.rand(5, top_k).half()
+    tw[:, 1] = 0
+    out = K().fused_moe(x.cuda(), w1.cuda(), w2.cuda(), tw.cuda(), ids.cuda())
+    close(out, ops.fused_moe(x, w1, w2, tw, ids), rtol=5e-3, atol=2e-3)
