@@ -59,11 +59,11 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      PipeState ps(p.stages);
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&ctl->empty[ps.stage], ps.phase ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    PipeState ps(p.stages);
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&ctl->empty[ps.stage], ps.phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&ctl->full[ps.stage], kABytes + kBBytes);
         const int kc = (kb0 + i) * kKPerStage;
         // weights are streamed exactly once: evict-first; activations are re-read by every CTA: evict-last
@@ -71,34 +71,38 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                          kEvictFirst);
         tma_load_2d_hint(b_ring + (size_t)ps.stage * kBBytes, &tmap_x, kc, m_tile * BT, &ctl->full[ps.stage],
                          kEvictLast);
-        ps.advance();
       }
+      __syncwarp();
+      ps.advance();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = KIND == 0
-          ? umma_idesc(1u, sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1u : 0u,
-                       std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, 0u, 0u, kBlockW, BT)
-          : umma_idesc(2u, 1u, 1u, 0u, 0u, kBlockW, BT);
-      PipeState ps(p.stages);
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&ctl->full[ps.stage], ps.phase);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(a_ring + (size_t)ps.stage * kABytes));
-        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(b_ring + (size_t)ps.stage * kBBytes));
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    constexpr uint32_t idesc = KIND == 0
+        ? umma_idesc(1u, std::is_same<T, __nv_bfloat16>::value ? 1u : 0u,
+                     std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, 0u, 0u, kBlockW, BT)
+        : umma_idesc(2u, 1u, 1u, 0u, 0u, kBlockW, BT);
+    const uint64_t a_desc0 = umma_desc_sw128_kmajor(smem_u32(a_ring));
+    const uint64_t b_desc0 = umma_desc_sw128_kmajor(smem_u32(b_ring));
+    PipeState ps(p.stages);
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&ctl->full[ps.stage], ps.phase);
+      tc_fence_after();
+      const uint64_t adesc = a_desc0 + (uint64_t)((ps.stage * kABytes) >> 4);
+      const uint64_t bdesc = b_desc0 + (uint64_t)((ps.stage * kBBytes) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // one MMA consumes 32 bytes of K per row: advance the start address by 2 (16-byte units)
           if (KIND == 0)
-            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
           else
-            umma_i8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+            umma_i8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
         }
         tc_commit(&ctl->empty[ps.stage]);  // frees the smem stage once these MMAs retire
-        ps.advance();
+        if (i + 1 == nkb) tc_commit(&ctl->acc_full[0]);
       }
-      tc_commit(&ctl->acc_full[0]);
+      __syncwarp();
+      ps.advance();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

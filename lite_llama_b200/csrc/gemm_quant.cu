@@ -174,12 +174,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      PipeState rs(p.raw_stages);
-      const int nrb = (nkb + RW - 1) / RW;
-      for (int rb = 0; rb < nrb; ++rb) {
-        mbar_wait(&ctl->raw_empty[rs.stage], rs.phase ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    PipeState rs(p.raw_stages);
+    const int nrb = (nkb + RW - 1) / RW;
+    for (int rb = 0; rb < nrb; ++rb) {
+      mbar_wait(&ctl->raw_empty[rs.stage], rs.phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&ctl->raw_full[rs.stage], kRawStage);   // OOB parts are zero-filled but still counted
         uint8_t* st = raw_ring + (size_t)rs.stage * kRawStage;
         const int kb = kb0 + rb * RW;                                  // first 64-element k-block of this raw block
@@ -190,52 +190,64 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int sub = 0; sub < RW; ++sub)
           tma_load_2d_hint(st + kABytes + sub * kXBytes, &tmap_x, (kb + sub) * 64, m_tile * BT,
                            &ctl->raw_full[rs.stage], kEvictLast);
-        rs.advance();
       }
+      __syncwarp();
+      rs.advance();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
-      const uint64_t ones_desc = umma_desc_sw128_kmajor(smem_u32(ones_tile));
-      PipeState rs(p.raw_stages), os(kOpStages);
-      int seg = 0;           // running segment index
-      int in_seg = 0;        // 16-element steps already issued into the open segment
-      int step = 0;          // global step index within this CTA's k-range
-      for (int i = 0; i < nkb; ++i) {
-        const int sub = i % RW;
-        if (sub == 0) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);   // activation sub-tiles (written by TMA)
-        mbar_wait(&ctl->op_full[os.stage], os.phase);    // dequantised weight tile
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(op_ring + (size_t)os.stage * kABytes));
-        const uint64_t bdesc = umma_desc_sw128_kmajor(
-            smem_u32(raw_ring + (size_t)rs.stage * kRawStage + kABytes + sub * kXBytes));
-#pragma unroll 1
-        for (int k = 0; k < 4 && step < steps_total; ++k, ++step) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
+    const uint64_t ones_desc = umma_desc_sw128_kmajor(smem_u32(ones_tile));
+    const uint64_t op_desc0 = umma_desc_sw128_kmajor(smem_u32(op_ring));
+    const uint64_t raw_desc0 = umma_desc_sw128_kmajor(smem_u32(raw_ring + kABytes));
+    PipeState rs(p.raw_stages), os(kOpStages);
+    const int seg_steps = seg_len / 16;
+    int steps_left = steps_total;                       // 16-element MMA steps still to issue
+    int seg_left = ((k_begin / seg_len + 1) * seg_len - k_begin) / 16;   // steps until the open segment closes
+    if (seg_left > steps_left) seg_left = steps_left;
+    int seg = 0;
+    bool seg_open = false;
+    for (int i = 0; i < nkb; ++i) {
+      const int sub = i % RW;
+      if (sub == 0) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);   // activation sub-tiles (written by TMA)
+      mbar_wait(&ctl->op_full[os.stage], os.phase);                  // dequantised weight tile
+      tc_fence_after();
+      // descriptors differ from the ring bases only in the 16-byte-unit start address field
+      const uint64_t adesc = op_desc0 + (uint64_t)((os.stage * kABytes) >> 4);
+      const uint64_t bdesc = raw_desc0 + (uint64_t)((rs.stage * kRawStage + sub * kXBytes) >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (steps_left > 0) {
           const int buf = seg & 1;
-          if (in_seg == 0) {
+          if (!seg_open) {
             // buffer `buf` was last drained for segment seg-2
             mbar_wait(&ctl->acc_empty[buf], ((seg >> 1) & 1) ^ 1);
             tc_fence_after();
           }
           const uint32_t d = tmem_base + buf * kAccCols;
-          umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, in_seg != 0);
-          if (QK == Q_INT4) umma_f16(d + BT, ones_desc + 2 * k, bdesc + 2 * k, idesc, in_seg != 0);
-          ++in_seg;
-          const int k_abs = k_begin + (step + 1) * 16;
-          if (k_abs % seg_len == 0 || step + 1 == steps_total) {
-            tc_commit(&ctl->acc_full[buf]);
+          --steps_left;
+          --seg_left;
+          const bool close = seg_left == 0;
+          if (elect_one()) {
+            umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, seg_open ? 1u : 0u);
+            if (QK == Q_INT4) umma_f16(d + BT, ones_desc + 2 * k, bdesc + 2 * k, idesc, seg_open ? 1u : 0u);
+            if (close) tc_commit(&ctl->acc_full[buf]);
+          }
+          seg_open = !close;
+          if (close) {
             ++seg;
-            in_seg = 0;
+            seg_left = seg_steps < steps_left ? seg_steps : steps_left;
           }
         }
-        tc_commit(&ctl->op_empty[os.stage]);
-        os.advance();
-        if (sub == RW - 1 || i + 1 == nkb) {
-          tc_commit(&ctl->raw_empty[rs.stage]);
-          rs.advance();
-        }
       }
+      const bool raw_done = (sub == RW - 1) || (i + 1 == nkb);
+      if (elect_one()) {
+        tc_commit(&ctl->op_empty[os.stage]);
+        if (raw_done) tc_commit(&ctl->raw_empty[rs.stage]);
+      }
+      __syncwarp();
+      os.advance();
+      if (raw_done) rs.advance();
     }
   } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
@@ -394,7 +406,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-constexpr int kMaxGroupsCta = 24;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
+constexpr int kMaxGroupsCta = 34;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
 
 static inline int groups_touched(int kb_per_split, int seg_len) {
   // worst case over split offsets: a k-range of kb_per_split*64 elements starting anywhere on a 64 boundary
@@ -422,8 +434,12 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
   }
   const int rw = qk == Q_INT4 ? 4 : 2;     // k-blocks per raw stage: splits must start on a raw-block boundary
   pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
-  // keep the per-CTA scale table bounded: more (smaller) splits when groups are fine-grained
-  while (pl.kb_per_split > rw && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) pl.kb_per_split -= rw;
+  // keep the per-CTA scale table bounded: more splits when groups are fine-grained -- but keep them BALANCED
+  // (equal k-ranges), an uneven last split would make one CTA of every tile the straggler
+  while (pl.kb_per_split > rw && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) {
+    ++splits;
+    pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
+  }
   pl.splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;
   const int max_groups = groups_touched(pl.kb_per_split, seg_len);
   const int raw_stage = kABytes + rw * pl.bt * kStageKBytes;

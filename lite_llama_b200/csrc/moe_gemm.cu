@@ -126,52 +126,66 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer: this expert's weight tile =====================
-    if (lane == 0) {
-      PipeState rs(p.raw_stages);
-      const int row0 = expert * p.N + n_tile * kBlockW;
-      const int nrb = (nkb + RW - 1) / RW;
-      for (int rb = 0; rb < nrb; ++rb) {
-        mbar_wait(&ctl->raw_empty[rs.stage], rs.phase ^ 1);
+    PipeState rs(p.raw_stages);
+    const int row0 = expert * p.N + n_tile * kBlockW;
+    const int nrb = (nkb + RW - 1) / RW;
+    for (int rb = 0; rb < nrb; ++rb) {
+      mbar_wait(&ctl->raw_empty[rs.stage], rs.phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&ctl->raw_full[rs.stage], kRawW);
         tma_load_2d_hint(raw_ring + (size_t)rs.stage * kRawW, &tmap_w, rb * RW * 64, row0, &ctl->raw_full[rs.stage],
                          kEvictFirst);
-        rs.advance();
       }
+      __syncwarp();
+      rs.advance();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
-      PipeState rs(p.raw_stages), os(kMoeOpStages);
-      int seg = 0, in_seg = 0, step = 0;
-      for (int i = 0; i < nkb; ++i) {
-        if (MK == M_F16) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);
-        mbar_wait(&ctl->op_full[os.stage], os.phase);
-        tc_fence_after();
-        const uint8_t* opst = op_ring + (size_t)os.stage * kOpStage;
-        const uint64_t adesc = umma_desc_sw128_kmajor(
-            smem_u32(MK == M_F16 ? raw_ring + (size_t)rs.stage * kRawW : opst));
-        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(opst + (MK == M_F16 ? 0 : kABytes)));
-#pragma unroll 1
-        for (int k = 0; k < 4 && step < steps_total; ++k, ++step) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
+    const uint64_t op_desc0 = umma_desc_sw128_kmajor(smem_u32(op_ring));
+    const uint64_t raw_desc0 = umma_desc_sw128_kmajor(smem_u32(raw_ring));
+    PipeState rs(p.raw_stages), os(kMoeOpStages);
+    const int seg_steps = seg_len / 16;
+    int steps_left = steps_total;
+    int seg_left = seg_steps < steps_left ? seg_steps : steps_left;
+    int seg = 0;
+    bool seg_open = false;
+    for (int i = 0; i < nkb; ++i) {
+      if (MK == M_F16) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);
+      mbar_wait(&ctl->op_full[os.stage], os.phase);
+      tc_fence_after();
+      const uint64_t opd = op_desc0 + (uint64_t)((os.stage * kOpStage) >> 4);
+      const uint64_t adesc = MK == M_F16 ? raw_desc0 + (uint64_t)((rs.stage * kRawW) >> 4) : opd;
+      const uint64_t bdesc = opd + (uint64_t)((MK == M_F16 ? 0 : kABytes) >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (steps_left > 0) {
           const int buf = seg & 1;
-          if (in_seg == 0) {
+          if (!seg_open) {
             mbar_wait(&ctl->acc_empty[buf], ((seg >> 1) & 1) ^ 1);
             tc_fence_after();
           }
-          umma_f16(tmem_base + buf * BT, adesc + 2 * k, bdesc + 2 * k, idesc, in_seg != 0);
-          ++in_seg;
-          if (((step + 1) * 16) % seg_len == 0 || step + 1 == steps_total) {
-            tc_commit(&ctl->acc_full[buf]);
+          --steps_left;
+          --seg_left;
+          const bool close = seg_left == 0;
+          if (elect_one()) {
+            umma_f16(tmem_base + buf * BT, adesc + 2 * k, bdesc + 2 * k, idesc, seg_open ? 1u : 0u);
+            if (close) tc_commit(&ctl->acc_full[buf]);
+          }
+          seg_open = !close;
+          if (close) {
             ++seg;
-            in_seg = 0;
+            seg_left = seg_steps < steps_left ? seg_steps : steps_left;
           }
         }
+      }
+      if (elect_one()) {
         tc_commit(&ctl->op_empty[os.stage]);
         if (MK == M_F16) tc_commit(&ctl->raw_empty[rs.stage]);
-        rs.advance();
-        os.advance();
       }
+      __syncwarp();
+      rs.advance();
+      os.advance();
     }
   } else if (warp < 6) {
     // ===================== epilogue =====================
@@ -345,7 +359,6 @@ extern "C" int b2l_moe_gemm(void* c, const void* a, const void* w, int weight_ki
   B2L_REQUIRE(c && a && w && sorted_token_ids && expert_ids && num_tokens_post_padded, "moe_gemm: null pointer");
   B2L_REQUIRE(weight_kind == M_F16 || weight_kind == M_FP8 || weight_kind == M_INT8, "moe_gemm: weight kind %d", weight_kind);
   B2L_REQUIRE(block_size == 16 || block_size == 32 || block_size == 64, "moe_gemm: block_size %d (16, 32 or 64)", block_size);
-  B2L_REQUIRE(em % block_size == 0, "moe_gemm: sorted ids length must be a multiple of block_size");
   B2L_REQUIRE(top_k >= 1 && num_experts >= 1 && n > 0 && k > 0, "moe_gemm: bad shape");
   B2L_REQUIRE(a_row_stride % 8 == 0 && (uintptr_t)a % 16 == 0 && k % 8 == 0, "moe_gemm: activations must be 16-byte aligned rows");
   B2L_REQUIRE(weight_kind == M_F16 || scales, "moe_gemm: quantised experts need scales");
@@ -376,7 +389,7 @@ extern "C" int b2l_moe_gemm(void* c, const void* a, const void* w, int weight_ki
     rc = b2l_make_tmap_2d(&tw, w, TMA_U8, (uint64_t)num_experts * n, (uint64_t)k, (uint64_t)w_row_stride, kBlockW, 128, true);
   if (rc != B2L_OK) return rc;
   const int n_tiles = (int)cdiv64(n, kBlockW);
-  const int max_blocks = (int)(em / block_size);
+  const int max_blocks = (int)((em + block_size - 1) / block_size);   // a trailing partial block is never < num_post
   cudaStream_t st = (cudaStream_t)stream;
 #define MOE_DISPATCH(MKV)                                                                      \
   switch (block_size) {                                                                        \
