@@ -6,24 +6,35 @@
 //   int4 : qweight int32 [N, K/8], nibble j of word i = K index 8i+j; scales, zeros fp32 [N, K/g]
 //   8-bit: qweight uint8(e4m3)/int8 [N, K]; scales fp32 [ceil(N/gn), ceil(K/gk)]
 //
-// Pipeline per CTA (see gemm_tc.cuh for the tile orientation):
-//   TMA producer   raw quantised weight tile + activation tile  -> deep "raw" ring (HBM latency hiding)
-//   8 dequant warps raw tile -> exact fp16 integers/e4m3 values -> UMMA operand ring (128B-swizzled, K-major)
-//   MMA issuer     tcgen05.mma per 16 K-elements into one of two TMEM accumulator buffers;
-//                  a buffer is closed at every scale-group boundary ("segment")
-//   4 epilogue warps drain each closed buffer:  acc += scale * (P - zero * xsum)   in fp32
+// Pipeline per CTA (tile orientation: gemm_tc.cuh -- 128 weight rows on the TMEM lanes, tokens on UMMA N):
+//   TMA producer     raw quantised weight tile (128 rows x 128 BYTES, 128B-swizzled) + the matching
+//                    activation sub-tiles -> deep shared-memory ring (HBM latency hiding)
+//   8 dequant warps  two groups of 4 warps alternate over the 64-element k-blocks; thread = weight row:
+//                    raw bytes -> exact fp16 values in registers -> tcgen05.st into a TMEM operand stage
+//   2 MMA issuers    tcgen05.mma with the A operand read from TENSOR MEMORY and B (activations) from
+//                    shared memory, accumulating into one of four TMEM accumulator buffers; a buffer is
+//                    closed at every scale-group boundary ("segment"); the two warps take alternate segments
+//   4 epilogue warps drain each closed buffer:  acc += scale * (P - zero * xsum)   in fp32; for int4 they also
+//                    compute xsum[m] = sum_k x[m,k] of the segment from the activation tiles in shared memory
+//
+// Why TMEM for the dequantised operand: staging it in shared memory (v2 of this kernel, see
+// profiles/) costs 16 KiB of st.shared + 16-32 KiB of tensor-core reads per 4 KiB of int4 fetched from
+// HBM -- an 8x traffic amplification that caps the kernel below the HBM roofline at the 128 B/clk/SM
+// shared-memory port.  In TMEM the operand never touches shared memory.
+//
 // Numerics: the tensor core multiplies the *unscaled* integer (or exact e4m3) weight values, so products
 // and the per-group partial sums are exact in fp32; scale and zero point are applied in fp32 afterwards,
-// exactly where the reference applies them (w4a16.py:104, w8a16.py:116).  For int4, xsum[m] = sum_k x[m,k]
-// over the segment comes from a second MMA against an all-ones tile, so it costs no CUDA-core work.
+// exactly where the reference applies them (w4a16.py:104, w8a16.py:116).
+// Measured history of this kernel (device timelines + ncu under profiles/): shared-memory operand staging,
+// per-segment global scale loads, single-lane role loops and serial barrier polling each capped it at
+// 5-20 % of HBM peak before the current structure.
 #include "gemm_tc.cuh"
 #include <type_traits>
 
 namespace gemm {
 
-constexpr int kDequantWarps = 8;
-constexpr int kQuantThreads = (2 + 4 + kDequantWarps) * 32;   // 448
-constexpr int kOpStages = 3;                                  // dequantised-operand ring depth
+constexpr int kQuantThreads = 16 * 32;      // producer, 2 MMA issuers, spare, 4 epilogue, 2 x 4 dequant warps
+constexpr int kAStages = 4;                 // max TMEM operand stages (one raw block each)
 constexpr int kMaxRawStages = 8;
 
 enum QuantKind { Q_INT4 = 0, Q_FP8 = 1, Q_INT8 = 2 };
@@ -39,41 +50,57 @@ struct QuantParams {
   int splits, kb_per_split, num_kb;
   int raw_stages;
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
+  int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
+  long long* timeline;                     // debug: [8 roles][256] clock64 stamps of CTA (0,0,0), or null
 };
+
+// role rows of the debug timeline
+enum { TL_PROD = 0, TL_MMA_READY = 1, TL_MMA_ISSUED = 2, TL_DQ_START = 3, TL_DQ_DONE = 4, TL_EPI_START = 5, TL_EPI_DONE = 6 };
+#define TL_STAMP(role, idx)                                                                   \
+  do {                                                                                        \
+    if (tl && (idx) < 256 && lane == 0) tl[(role) * 256 + (idx)] = clock64();                 \
+  } while (0)
 
 struct __align__(8) QControl {
   uint64_t raw_full[kMaxRawStages];
   uint64_t raw_empty[kMaxRawStages];
-  uint64_t op_full[kOpStages];
-  uint64_t op_empty[kOpStages];
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
+  uint64_t op_full[kAStages];
+  uint64_t op_empty[kAStages];
+  uint64_t acc_full[4];
+  int epi_done[4];                         // per epilogue warp: number of segments whose accumulator it has drained
   uint32_t tmem_base;
   int is_last;
 };
 static_assert(sizeof(QControl) <= 1024, "control block too large");
 
-// A raw stage holds 128 weight rows x 128 BYTES of quantised K (TMA needs full 128-byte rows to stream
-// HBM efficiently: with 32/64-byte rows the first version reached 5-10 % of peak) = RW operand k-blocks
-// of 64 elements (int4: 256 elements -> 4, 8-bit: 128 -> 2), plus the RW activation sub-tiles.
+// Four TMEM accumulator buffers: the epilogue's drain latency (wake-up, tcgen05.ld, FMAs, arrive) is several
+// hundred cycles per segment; with only two buffers the MMA warps stalled on acc_empty (ncu: profiles/).
+
+// A raw stage holds 128 weight rows x 128 BYTES of quantised K (TMA needs full 128-byte rows to stream HBM
+// efficiently) = RW operand k-blocks of 64 elements (int4: 256 elements -> 4, 8-bit: 128 -> 2), followed by
+// the RW activation sub-tiles [BT x 64] (128B-swizzled, K-major: the UMMA B operand).
 template <int QK> __host__ __device__ constexpr int raw_sub() { return QK == Q_INT4 ? 4 : 2; }
 template <int QK, int BT> __host__ __device__ constexpr int raw_stage_bytes() {
   return kABytes + raw_sub<QK>() * BT * kStageKBytes;
 }
+// TMEM operand stages that fit next to the four accumulator buffers (512 columns in total)
+template <int QK, int BT> __host__ __device__ constexpr int a_stages() {
+  return (512 - 4 * BT) / (raw_sub<QK>() * 32) < kAStages ? (512 - 4 * BT) / (raw_sub<QK>() * 32) : kAStages;
+}
 
-// ---- dequantisers: 8 packed weights -> 8 fp16 values in K order (one 16-byte operand chunk) ----
+// ---- dequantisers: packed weights -> fp16 pairs in K order (one 32-bit TMEM column per pair) ----
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(mask), "r"(orv));  // (a & mask) | orv
   return r;
 }
-__device__ __forceinline__ uint4 dequant_int4_word(uint32_t w) {
+// one int32 word (8 nibbles) -> 4 half2 {n0,n1} {n2,n3} {n4,n5} {n6,n7}
+__device__ __forceinline__ void dequant_int4_word(uint32_t w, uint32_t* out) {
   // byte j holds nibbles (2j, 2j+1).  Replicate the byte into both halves, keep nibble 2j in the low
   // half's mantissa and nibble 2j+1 (still shifted left by 4) in the high half's, OR in the fp16
   // exponent of 1024: low = 1024 + n0, high = 1024 + 16*n1; one HFMA2 maps both back to exact integers.
   const __half2 mul = __halves2half2(__float2half(1.0f), __float2half(0.0625f));
   const __half2 add = __halves2half2(__float2half(-1024.0f), __float2half(-64.0f));
-  uint32_t out[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t rep = __byte_perm(w, w, 0x1111 * j);
@@ -81,33 +108,74 @@ __device__ __forceinline__ uint4 dequant_int4_word(uint32_t w) {
     const __half2 v = __hfma2(*reinterpret_cast<const __half2*>(&h), mul, add);
     out[j] = *reinterpret_cast<const uint32_t*>(&v);
   }
-  return make_uint4(out[0], out[1], out[2], out[3]);
 }
 __device__ __forceinline__ uint32_t cvt_e4m3x2_f16x2(uint16_t v) {
   uint32_t r;
   asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"(v));
   return r;
 }
-__device__ __forceinline__ uint4 dequant_fp8_8(uint32_t lo, uint32_t hi) {
-  return make_uint4(cvt_e4m3x2_f16x2((uint16_t)(lo & 0xFFFFu)), cvt_e4m3x2_f16x2((uint16_t)(lo >> 16)),
-                    cvt_e4m3x2_f16x2((uint16_t)(hi & 0xFFFFu)), cvt_e4m3x2_f16x2((uint16_t)(hi >> 16)));
-}
-__device__ __forceinline__ uint4 dequant_int8_8(uint32_t lo, uint32_t hi) {
-  // b -> u = b + 128 (xor 0x80), fp16(0x6400 | u) = 1024 + u, minus 1152 = b   (all exact)
-  const __half2 off = __float2half2_rn(-1152.0f);
-  uint32_t out[4];
-  const uint32_t ul = lo ^ 0x80808080u, uh = hi ^ 0x80808080u;
-  const uint32_t src[2] = {ul, uh};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t sel = (j & 1) ? 0x4342u : 0x4140u;   // [0x64, byte(2i+1), 0x64, byte(2i)]
-    const uint32_t h = __byte_perm(src[j >> 1], 0x64646464u, sel);
-    const __half2 v = __hadd2(*reinterpret_cast<const __half2*>(&h), off);
-    out[j] = *reinterpret_cast<const uint32_t*>(&v);
+// one 32-bit word (4 bytes) -> 2 half2
+__device__ __forceinline__ void dequant_w8_word(uint32_t w, bool fp8, uint32_t* out) {
+  if (fp8) {
+    out[0] = cvt_e4m3x2_f16x2((uint16_t)(w & 0xFFFFu));
+    out[1] = cvt_e4m3x2_f16x2((uint16_t)(w >> 16));
+  } else {
+    // b -> u = b + 128 (xor 0x80), fp16(0x6400 | u) = 1024 + u, minus 1152 = b   (all exact)
+    const __half2 off = __float2half2_rn(-1152.0f);
+    const uint32_t u = w ^ 0x80808080u;
+    const uint32_t h0 = __byte_perm(u, 0x64646464u, 0x4140u);   // [0x64, byte1, 0x64, byte0]
+    const uint32_t h1 = __byte_perm(u, 0x64646464u, 0x4342u);
+    const __half2 v0 = __hadd2(*reinterpret_cast<const __half2*>(&h0), off);
+    const __half2 v1 = __hadd2(*reinterpret_cast<const __half2*>(&h1), off);
+    out[0] = *reinterpret_cast<const uint32_t*>(&v0);
+    out[1] = *reinterpret_cast<const uint32_t*>(&v1);
   }
-  return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// registers -> TMEM: lane of the warp writes its own TMEM lane, 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]   (A: 128 lanes x 8 columns = 128 x 16 fp16, K-major)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_smem(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_smem(int* p, int v) {
+  asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// Granularity (measured with the device timeline, profiles/): every mbarrier hand-off costs the MMA warp
+// 100-200 cycles and every UTCHMMA ~50, so one hand-off per 64-element k-block (4 MMAs) left the issuer at
+// ~600 cycles per k-block while HBM can deliver an int4 k-block tile every ~180.  The unit of hand-off is
+// therefore a whole RAW BLOCK (one 128-byte-wide TMA tile: 256 int4 / 128 8-bit K values = 16 / 8 MMAs):
+// the 8 dequant warps fill one TMEM operand stage per raw block, two MMA warps take alternate raw blocks,
+// and "accumulator drained" is a plain shared-memory counter per epilogue warp instead of an mbarrier.
 template <int QK, int BT>
 __global__ void __launch_bounds__(kQuantThreads, 1)
 gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -116,57 +184,61 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   QControl* ctl = reinterpret_cast<QControl*>(smem);
-  uint8_t* ones_tile = smem + 1024;                               // int4: 128 x 64 fp16 ones (16 KiB)
-  uint8_t* op_ring = ones_tile + (QK == Q_INT4 ? kABytes : 0);    // kOpStages x 16 KiB
-  uint8_t* raw_ring = op_ring + kOpStages * kABytes;              // raw_stages x (X tile, raw W tile)
-  constexpr int kXBytes = BT * kStageKBytes;          // one activation sub-tile (64 K elements)
-  constexpr int RW = raw_sub<QK>();
-  constexpr int kRawStage = raw_stage_bytes<QK, BT>(); // [raw W 16 KiB (128B-swizzled)] [RW x X sub-tile]
-  // per-row scale (and zero-point) table of this CTA's k-range: [group][128 rows] fp32, filled once with
-  // cp.async by the epilogue threads (each thread only ever touches its own column -> no barrier needed)
+  uint8_t* raw_ring = smem + 1024;                     // raw_stages x [raw W 16 KiB | RW x X sub-tile]
+  constexpr int kXBytes = BT * kStageKBytes;           // one activation sub-tile (64 K elements)
+  constexpr int RW = raw_sub<QK>();                    // 64-element k-blocks per raw block
+  constexpr int kRawK = RW * 64;
+  constexpr int kRawStage = raw_stage_bytes<QK, BT>();
+  // per-row scale (and zero-point) table of this CTA's k-range, row-major [128 rows][tab_pitch] fp32, filled
+  // once with cp.async by the epilogue threads (each thread only touches its own row -> no barrier needed)
   float* scale_tab = reinterpret_cast<float*>(raw_ring + (size_t)p.raw_stages * kRawStage);
-  float* zero_tab = scale_tab + (size_t)p.max_groups * kBlockW;
-  constexpr int kAccCols = QK == Q_INT4 ? 2 * BT : BT;            // per buffer: P (+ xsum)
-  constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+  const int tab_pitch = p.max_groups;                  // multiple of 4 floats
+  float* zero_tab = scale_tab + (size_t)tab_pitch * kBlockW;
+  float* xs_smem = zero_tab + (QK == Q_INT4 ? (size_t)tab_pitch * kBlockW : 0);   // [2][BT] per-segment xsum exchange
+  // TMEM map (columns): [NB accumulator buffers of BT] [NA operand stages of RW*32]
+  constexpr int NB = 4;
+  constexpr int kAStageCols = RW * 32;
+  constexpr int NA = a_stages<QK, BT>();
+  constexpr int kAColBase = NB * BT;
+  constexpr int kColsUsed = kAColBase + NA * kAStageCols;
+  constexpr int kTmemCols = kColsUsed <= 32 ? 32 : kColsUsed <= 64 ? 64 : kColsUsed <= 128 ? 128
+                          : kColsUsed <= 256 ? 256 : 512;
+  static_assert(kColsUsed <= 512 && NA >= 2, "TMEM budget exceeded");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  long long* tl = (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.timeline : nullptr;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
   const int nkb = kb1 - kb0;
+  const int nrb = (nkb + RW - 1) / RW;            // raw blocks of this CTA
   const int seg_len = p.group_k;                  // K elements per scale group (multiple of 16)
   const int k_begin = kb0 * 64;
   int k_end = kb1 * 64; if (k_end > p.K) k_end = p.K;
   // segments: maximal runs of 16-element MMA steps inside one scale group and inside [k_begin, k_end)
   const int steps_total = (k_end - k_begin + 15) / 16;
+  // two MMA warps (alternate raw blocks) when no segment spans two raw blocks, else warp 1 alone
+  const int mma_warps = p.aligned ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < p.raw_stages; ++s) {
       mbar_init(&ctl->raw_full[s], 1);
-      mbar_init(&ctl->raw_empty[s], kDequantWarps + 1);
+      // released by: 8 dequant warps, the MMA warp that owns the block, and (int4) the 4 epilogue warps
+      mbar_init(&ctl->raw_empty[s], 8 + 1 + (QK == Q_INT4 ? 4 : 0));
     }
-    for (int s = 0; s < kOpStages; ++s) {
-      mbar_init(&ctl->op_full[s], kDequantWarps);
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&ctl->op_full[s], 8);
       mbar_init(&ctl->op_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], 4);
-    }
+    for (int s = 0; s < NB; ++s) mbar_init(&ctl->acc_full[s], 1);
+    for (int q = 0; q < 4; ++q) ctl->epi_done[q] = 0;
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, kTmemCols);
     tmem_relinquish();
-  }
-  if (QK == Q_INT4 && warp >= 6) {
-    // fill the all-ones operand tile (layout-independent: every element is 1.0)
-    const uint32_t one2 = 0x3C003C00u;
-    uint4* dst = reinterpret_cast<uint4*>(ones_tile);
-    for (int i = threadIdx.x - 6 * 32; i < kABytes / 16; i += kDequantWarps * 32) dst[i] = make_uint4(one2, one2, one2, one2);
-    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -176,14 +248,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     PipeState rs(p.raw_stages);
-    const int nrb = (nkb + RW - 1) / RW;
     for (int rb = 0; rb < nrb; ++rb) {
       mbar_wait(&ctl->raw_empty[rs.stage], rs.phase ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&ctl->raw_full[rs.stage], kRawStage);   // OOB parts are zero-filled but still counted
         uint8_t* st = raw_ring + (size_t)rs.stage * kRawStage;
         const int kb = kb0 + rb * RW;                                  // first 64-element k-block of this raw block
-        // raw weight tile: 128 rows x 128 bytes (int4: 32 int32 words = 256 K; 8-bit: 128 K), 128B-swizzled
         tma_load_2d_hint(st, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64, n_tile * kBlockW, &ctl->raw_full[rs.stage],
                          kEvictFirst);
 #pragma unroll
@@ -192,65 +262,77 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                            &ctl->raw_full[rs.stage], kEvictLast);
       }
       __syncwarp();
+      TL_STAMP(TL_PROD, rb);
       rs.advance();
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
-    const uint64_t ones_desc = umma_desc_sw128_kmajor(smem_u32(ones_tile));
-    const uint64_t op_desc0 = umma_desc_sw128_kmajor(smem_u32(op_ring));
-    const uint64_t raw_desc0 = umma_desc_sw128_kmajor(smem_u32(raw_ring + kABytes));
-    PipeState rs(p.raw_stages), os(kOpStages);
-    const int seg_steps = seg_len / 16;
-    int steps_left = steps_total;                       // 16-element MMA steps still to issue
-    int seg_left = ((k_begin / seg_len + 1) * seg_len - k_begin) / 16;   // steps until the open segment closes
-    if (seg_left > steps_left) seg_left = steps_left;
-    int seg = 0;
-    bool seg_open = false;
-    for (int i = 0; i < nkb; ++i) {
-      const int sub = i % RW;
-      if (sub == 0) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);   // activation sub-tiles (written by TMA)
-      mbar_wait(&ctl->op_full[os.stage], os.phase);                  // dequantised weight tile
-      tc_fence_after();
-      // descriptors differ from the ring bases only in the 16-byte-unit start address field
-      const uint64_t adesc = op_desc0 + (uint64_t)((os.stage * kABytes) >> 4);
-      const uint64_t bdesc = raw_desc0 + (uint64_t)((rs.stage * kRawStage + sub * kXBytes) >> 4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (steps_left > 0) {
-          const int buf = seg & 1;
-          if (!seg_open) {
-            // buffer `buf` was last drained for segment seg-2
-            mbar_wait(&ctl->acc_empty[buf], ((seg >> 1) & 1) ^ 1);
-            tc_fence_after();
-          }
-          const uint32_t d = tmem_base + buf * kAccCols;
-          --steps_left;
-          --seg_left;
-          const bool close = seg_left == 0;
-          if (elect_one()) {
-            umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, seg_open ? 1u : 0u);
-            if (QK == Q_INT4) umma_f16(d + BT, ones_desc + 2 * k, bdesc + 2 * k, idesc, seg_open ? 1u : 0u);
-            if (close) tc_commit(&ctl->acc_full[buf]);
-          }
-          seg_open = !close;
-          if (close) {
-            ++seg;
-            seg_left = seg_steps < steps_left ? seg_steps : steps_left;
-          }
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers =====================
+    if (warp - 1 < mma_warps) {
+      constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
+      const uint64_t x_desc0 = umma_desc_sw128_kmajor(smem_u32(raw_ring + kABytes));
+      const uint32_t a_base = tmem_base + kAColBase;
+      const int seg_steps = seg_len / 16;
+      // running segment state (only the elected lane's copy is ever used; election always picks the same lane)
+      int seg = 0;
+      int seg_left = ((k_begin / seg_len + 1) * seg_len - k_begin) / 16;   // steps until the open segment closes
+      if (seg_left > steps_total) seg_left = steps_total;
+      bool seg_open = false;
+      for (int rb = warp - 1; rb < nrb; rb += mma_warps) {
+        const int rstage = rb % p.raw_stages, ostage = rb % NA;
+        TL_STAMP(7, rb);
+        mbar_wait(&ctl->op_full[ostage], (rb / NA) & 1);                 // dequantised operand (8 dequant warps)
+        mbar_wait(&ctl->raw_full[rstage], (rb / p.raw_stages) & 1);      // activation sub-tiles (TMA)
+        tc_fence_after();
+        TL_STAMP(TL_MMA_READY, rb);
+        int steps_here = steps_total - rb * (RW * 4);
+        if (steps_here > RW * 4) steps_here = RW * 4;
+        if (mma_warps == 2) {
+          // raw blocks hold whole segments in this mode: state restarts at the block boundary
+          seg = rb * (kRawK / seg_len);
+          seg_left = seg_steps < steps_here ? seg_steps : steps_here;
+          seg_open = false;
         }
+        if (elect_one()) {
+          const uint64_t bdesc0 = x_desc0 + (uint64_t)((rstage * kRawStage) >> 4);
+          const uint32_t a0 = a_base + ostage * kAStageCols;
+#pragma unroll
+          for (int st = 0; st < RW * 4; ++st) {
+            if (st < steps_here) {
+              const int buf = seg % NB;
+              if (!seg_open && seg >= NB) {
+                // accumulator buffer `buf` must have been drained for segment seg-NB by all four epilogue warps
+                const int need = seg - NB + 1;
+                while (ld_acquire_smem(&ctl->epi_done[0]) < need || ld_acquire_smem(&ctl->epi_done[1]) < need ||
+                       ld_acquire_smem(&ctl->epi_done[2]) < need || ld_acquire_smem(&ctl->epi_done[3]) < need) {
+                }
+                tc_fence_after();
+              }
+              const uint64_t bdesc = bdesc0 + (uint64_t)(((st >> 2) * kXBytes) >> 4) + 2 * (st & 3);
+              umma_f16_ts(tmem_base + buf * BT, a0 + st * 8, bdesc, idesc, seg_open ? 1u : 0u);
+              --seg_left;
+              if (seg_left == 0) {
+                tc_commit(&ctl->acc_full[buf]);
+                ++seg;
+                seg_open = false;
+                // the next segment may extend beyond this raw block (single-warp mode); it is cut by the k-range end only
+                const int total_left = steps_total - rb * (RW * 4) - (st + 1);
+                seg_left = seg_steps < total_left ? seg_steps : total_left;
+              } else {
+                seg_open = true;
+              }
+            }
+          }
+          tc_commit(&ctl->op_empty[ostage]);
+          tc_commit(&ctl->raw_empty[rstage]);
+        }
+        __syncwarp();
+        TL_STAMP(TL_MMA_ISSUED, rb);
       }
-      const bool raw_done = (sub == RW - 1) || (i + 1 == nkb);
-      if (elect_one()) {
-        tc_commit(&ctl->op_empty[os.stage]);
-        if (raw_done) tc_commit(&ctl->raw_empty[rs.stage]);
-      }
-      __syncwarp();
-      os.advance();
-      if (raw_done) rs.advance();
     }
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5) =====================
+  } else if (warp == 3) {
+    // spare warp (keeps the epilogue warps on a 4-aligned warp id so that warp % 4 == TMEM lane quadrant)
+  } else if (warp < 8) {
+    // ===================== epilogue (warps 4..7) =====================
     const int quad = warp & 3;
     const int epi_tid = quad * 32 + lane;
     const int n = n_tile * kBlockW + epi_tid;
@@ -261,64 +343,117 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
     for (int j = 0; j < BT; ++j) acc[j] = 0.f;
 
-    // stage this row's scales / zero points for every group of the CTA's k-range (asynchronously:
-    // a per-segment global load would put a DRAM round trip on the drain's critical path)
+    // stage this row's scales / zero points for every group of the CTA's k-range with cp.async (a per-segment
+    // global load would put a DRAM round trip on the drain's critical path); 16 bytes (4 groups) per copy when
+    // the row is contiguous and aligned.  The wait is deferred until the first accumulator is ready.
     const int g_first = k_begin / seg_len;
-    {
-      const int g_last = (k_begin + steps_total * 16 - 1) / seg_len;
-      if (n_ok) {
-        const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n;
-        const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n : nullptr;
-        for (int g = g_first; g <= g_last; ++g) {
-          const int slot = (g - g_first) * kBlockW + epi_tid;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(scale_tab + slot)),
-                       "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
+    const int g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+    if (n_ok) {
+      const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g_first * p.s_stride_k;
+      const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n + (int64_t)g_first * p.s_stride_k : nullptr;
+      float* sdst = scale_tab + epi_tid * tab_pitch;
+      float* zdst = zero_tab + epi_tid * tab_pitch;
+      const bool vec = p.s_stride_k == 1 && ((uintptr_t)srow % 16 == 0) && (QK != Q_INT4 || (uintptr_t)zrow % 16 == 0);
+      int g = 0;
+      if (vec) {
+        for (; g + 4 <= g_count; g += 4) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + g)), "l"(srow + g) : "memory");
           if (QK == Q_INT4)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zero_tab + slot)),
-                         "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(zdst + g)), "l"(zrow + g) : "memory");
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      for (; g < g_count; ++g) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst + g)),
+                     "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
+        if (QK == Q_INT4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zdst + g)),
+                       "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
-    // enumerate segments exactly like the MMA warp does
+    // int4: xsum[m] = sum over the segment of x[m, k], computed here from the activation sub-tiles the TMA put
+    // in shared memory (thread -> token m = tid / PARTS, an interleaved share of the segment's 16-byte chunks)
+    constexpr int PARTS = 128 / BT;
+    const int xs_m = epi_tid / PARTS, xs_part = epi_tid % PARTS;
+
+    // enumerate segments exactly like the MMA warps do
     int k_pos = k_begin;
     int seg = 0;
-    while (k_pos < k_begin + steps_total * 16) {
+    const int k_lim = k_begin + steps_total * 16;
+    while (k_pos < k_lim) {
       int k_next = (k_pos / seg_len + 1) * seg_len;
-      const int k_lim = k_begin + steps_total * 16;
       if (k_next > k_lim) k_next = k_lim;
       const int g = k_pos / seg_len;
+      float xsum_m = 0.f;
+      if (QK == Q_INT4) {
+        const int c_begin = (k_pos - k_begin) / 8, c_end = (k_next - k_begin) / 8;   // 8-element chunks of the k-range
+        // walk the raw blocks covering this segment one at a time (a segment may be longer than the ring):
+        // wait for the block, add this thread's chunks of it, release it as soon as the k-range is past its end
+        const int rb_lo = (k_pos - k_begin) / kRawK, rb_hi = (k_next - 1 - k_begin) / kRawK;
+        for (int rb = rb_lo; rb <= rb_hi; ++rb) {
+          mbar_wait(&ctl->raw_full[rb % p.raw_stages], (rb / p.raw_stages) & 1);
+          const int lo = c_begin > rb * (kRawK / 8) ? c_begin : rb * (kRawK / 8);
+          const int hi = c_end < (rb + 1) * (kRawK / 8) ? c_end : (rb + 1) * (kRawK / 8);
+          const uint8_t* xbase = raw_ring + (size_t)(rb % p.raw_stages) * kRawStage + kABytes + xs_m * 128;
+          for (int c = lo + xs_part; c < hi; c += PARTS) {
+            const int sub = (c >> 3) % RW, ch = c & 7;               // sub-tile (k-block) and 16-byte chunk of the row
+            const uint4 v = *reinterpret_cast<const uint4*>(xbase + sub * kXBytes + ((ch ^ (xs_m & 7)) << 4));
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(h[q]);
+              xsum_m += f.x + f.y;
+            }
+          }
+          if (c_end >= (rb + 1) * (kRawK / 8) || k_next == k_lim) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->raw_empty[rb % p.raw_stages]);
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < PARTS && o < 32; o <<= 1) xsum_m += __shfl_xor_sync(0xffffffffu, xsum_m, o);
+        // exchange: every thread needs all BT sums
+        float* xs = xs_smem + (seg & 1) * BT;
+        if (xs_part == 0) xs[xs_m] = xsum_m;
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+      }
+      const int buf = seg % NB;
+      mbar_wait(&ctl->acc_full[buf], (seg / NB) & 1);
+      tc_fence_after();
+      if (warp == 4) TL_STAMP(TL_EPI_START, seg);
+      if (seg == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");   // own copies only: no barrier needed
       float sc = 0.f, zp = 0.f;
       if (n_ok) {
-        sc = scale_tab[(g - g_first) * kBlockW + epi_tid];
-        if (QK == Q_INT4) zp = zero_tab[(g - g_first) * kBlockW + epi_tid];
+        sc = scale_tab[epi_tid * tab_pitch + (g - g_first)];
+        if (QK == Q_INT4) zp = zero_tab[epi_tid * tab_pitch + (g - g_first)];
       }
-      const int buf = seg & 1;
-      mbar_wait(&ctl->acc_full[buf], (seg >> 1) & 1);
-      tc_fence_after();
-      const uint32_t ta = taddr + buf * kAccCols;
+      const uint32_t ta = taddr + buf * BT;
+      const float4* xs4 = reinterpret_cast<const float4*>(xs_smem + (seg & 1) * BT);
 #pragma unroll
       for (int c = 0; c < BT; c += 16) {
         uint32_t pv[16];
         tmem_ld_32x32b_x16(ta + c, pv);
+        tc_wait_ld();
         if (QK == Q_INT4) {
-          uint32_t xs[16];
-          tmem_ld_32x32b_x16(ta + BT + c, xs);
-          tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            acc[c + j] = fmaf(sc, fmaf(-zp, __uint_as_float(xs[j]), __uint_as_float(pv[j])), acc[c + j]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 x4 = xs4[(c >> 2) + j4];
+            acc[c + 4 * j4 + 0] = fmaf(sc, fmaf(-zp, x4.x, __uint_as_float(pv[4 * j4 + 0])), acc[c + 4 * j4 + 0]);
+            acc[c + 4 * j4 + 1] = fmaf(sc, fmaf(-zp, x4.y, __uint_as_float(pv[4 * j4 + 1])), acc[c + 4 * j4 + 1]);
+            acc[c + 4 * j4 + 2] = fmaf(sc, fmaf(-zp, x4.z, __uint_as_float(pv[4 * j4 + 2])), acc[c + 4 * j4 + 2]);
+            acc[c + 4 * j4 + 3] = fmaf(sc, fmaf(-zp, x4.w, __uint_as_float(pv[4 * j4 + 3])), acc[c + 4 * j4 + 3]);
+          }
         } else {
-          tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c + j]);
         }
       }
+      // this warp's quadrant of accumulator buffer `buf` is drained: publish (release) the count
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+      if (lane == 0) st_release_smem(&ctl->epi_done[quad], seg + 1);
+      if (warp == 4) TL_STAMP(TL_EPI_DONE, seg);
       k_pos = k_next;
       ++seg;
     }
@@ -354,50 +489,55 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
   } else {
-    // ===================== dequant warps (6..13) =====================
-    const int dt = threadIdx.x - 6 * 32;          // 0..255
-    // 8 consecutive threads = 8 consecutive rows: their 16-byte accesses hit 8 different swizzled chunks,
-    // so both the raw-tile loads and the operand-tile stores are bank-conflict free
-    const int row = dt & 127, hsel = dt >> 7;
+    // ===================== dequant warps 8..15: thread = one weight row, half of each raw block =====================
+    // A warp may only touch the TMEM lane quadrant (warp id % 4).  Warps 8..11 convert the first half of
+    // the raw block's K range, warps 12..15 the second half; all eight arrive on the operand stage's barrier.
+    const int half = (warp - 8) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
     const int rx = row & 7;
-    PipeState rs(p.raw_stages), os(kOpStages);
-    for (int i = 0; i < nkb; ++i) {
-      const int sub = i % RW;
-      if (sub == 0) mbar_wait(&ctl->raw_full[rs.stage], rs.phase);
-      mbar_wait(&ctl->op_empty[os.stage], os.phase ^ 1);
-      const uint8_t* rawrow = raw_ring + (size_t)rs.stage * kRawStage + row * 128;
-      uint8_t* arow = op_ring + (size_t)os.stage * kABytes + row * 128;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int rb = 0; rb < nrb; ++rb) {
+      const int rstage = rb % p.raw_stages, ostage = rb % NA;
+      mbar_wait(&ctl->raw_full[rstage], (rb / p.raw_stages) & 1);
+      mbar_wait(&ctl->op_empty[ostage], ((rb / NA) & 1) ^ 1);
+      tc_fence_after();
+      if (quad == 0 && half == 0) TL_STAMP(TL_DQ_START, rb);
+      const uint8_t* rawrow = raw_ring + (size_t)rstage * kRawStage + row * 128;
+      const uint32_t a_stage = lane_base + kAColBase + ostage * kAStageCols;
       if (QK == Q_INT4) {
-        // this k-block's 64 nibbles of the row = logical 16-byte chunks 2*sub, 2*sub+1; this thread takes one
-        const uint4 w4 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2 + hsel) ^ rx) << 4));
-        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        // 128 raw bytes per row = 8 logical 16-byte chunks (swizzled by row & 7) = 4 k-blocks; this warp: 2 of them
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = hsel * 4 + j;
-          *reinterpret_cast<uint4*>(arow + ((chunk ^ (row & 7)) << 4)) = dequant_int4_word(ws[j]);
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const int sub = half * 2 + s2;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2) ^ rx) << 4));
+          const uint4 w1 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2 + 1) ^ rx) << 4));
+          const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          uint32_t vals[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], vals + 4 * j);
+          tmem_st_32x32b_x32(a_stage + sub * 32, vals);
         }
       } else {
-        // this k-block's 64 bytes of the row = logical chunks 4*sub .. 4*sub+3; this thread takes two
-        const int c0 = sub * 4 + hsel * 2;
-        const uint4 lo4 = *reinterpret_cast<const uint4*>(rawrow + ((c0 ^ rx) << 4));
-        const uint4 hi4 = *reinterpret_cast<const uint4*>(rawrow + (((c0 + 1) ^ rx) << 4));
-        const uint32_t ws[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        // 128 raw bytes per row = 2 k-blocks of 64 bytes; this warp: one of them (4 chunks)
+        uint32_t vals[32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = hsel * 4 + j;
-          const uint4 v = QK == Q_FP8 ? dequant_fp8_8(ws[2 * j], ws[2 * j + 1]) : dequant_int8_8(ws[2 * j], ws[2 * j + 1]);
-          *reinterpret_cast<uint4*>(arow + ((chunk ^ (row & 7)) << 4)) = v;
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = *reinterpret_cast<const uint4*>(rawrow + (((half * 4 + c) ^ rx) << 4));
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dequant_w8_word(ws[j], QK == Q_FP8, vals + 8 * c + 2 * j);
         }
+        tmem_st_32x32b_x32(a_stage + half * 32, vals);
       }
-      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async proxy
+      tc_wait_st();
+      tc_fence_before();
       __syncwarp();
-      const bool raw_done = (sub == RW - 1) || (i + 1 == nkb);
       if (lane == 0) {
-        mbar_arrive(&ctl->op_full[os.stage]);
-        if (raw_done) mbar_arrive(&ctl->raw_empty[rs.stage]);
+        mbar_arrive(&ctl->op_full[ostage]);
+        mbar_arrive(&ctl->raw_empty[rstage]);     // raw bytes are in registers/TMEM now
       }
-      os.advance();
-      if (raw_done) rs.advance();
+      if (quad == 0 && half == 0) TL_STAMP(TL_DQ_DONE, rb);
     }
   }
 
@@ -406,12 +546,14 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-constexpr int kMaxGroupsCta = 34;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
+static long long* g_timeline = nullptr;   // set through b2l_debug_set_timeline (tools/timeline.py)
+
+constexpr int kMaxGroupsCta = 40;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
 
 static inline int groups_touched(int kb_per_split, int seg_len) {
   // worst case over split offsets: a k-range of kb_per_split*64 elements starting anywhere on a 64 boundary
   const int span = kb_per_split * 64;
-  return (span + seg_len - 1) / seg_len + 1;
+  return ((span + seg_len - 1) / seg_len + 1 + 3) / 4 * 4;   // table pitch: whole 16-byte chunks
 }
 
 static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int seg_len) {
@@ -443,8 +585,7 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
   pl.splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;
   const int max_groups = groups_touched(pl.kb_per_split, seg_len);
   const int raw_stage = kABytes + rw * pl.bt * kStageKBytes;
-  const int fixed = 1024 + (qk == Q_INT4 ? kABytes : 0) + kOpStages * kABytes + 1024 +
-                    max_groups * kBlockW * 4 * (qk == Q_INT4 ? 2 : 1);
+  const int fixed = 1024 + 1024 + 1024 /*xsum exchange*/ + max_groups * kBlockW * 4 * (qk == Q_INT4 ? 2 : 1);
   int stages = (b2l_max_smem_optin() - fixed) / raw_stage;
   if (stages > kMaxRawStages) stages = kMaxRawStages;
   if (stages > pl.kb_per_split / rw + 1) stages = pl.kb_per_split / rw + 1;
@@ -487,6 +628,9 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   p.max_groups = groups_touched(pl.kb_per_split, seg_len);
   p.y = y; p.ldy = y_row_stride; p.M = (int)m; p.N = (int)n; p.K = (int)k;
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.num_kb = pl.num_kb; p.raw_stages = pl.stages;
+  p.timeline = g_timeline;
+  // two MMA warps on alternate raw blocks are only legal when no segment spans two raw blocks
+  p.aligned = ((qk == Q_INT4 ? 256 : 128) % seg_len == 0);
   p.ws = (uint32_t*)workspace; p.counters = (int*)counters;
   if (pl.splits > 1) {
     const int64_t need = (int64_t)pl.n_tiles * pl.m_tiles * pl.splits * pl.bt * kBlockW * 4;
@@ -517,6 +661,13 @@ static inline int seg_len_for(int kind, int64_t k, int64_t group_k) {
   return (int)((gk + 15) / 16 * 16);
 }
 
+// Debug hook: device buffer of 8*256 int64 receiving clock64 stamps from CTA (0,0,0) of the next quantised
+// GEMM launches (null disables).  Not part of the product path.
+extern "C" int b2l_debug_set_timeline(void* device_buffer) {
+  gemm::g_timeline = (long long*)device_buffer;
+  return B2L_OK;
+}
+
 extern "C" int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k, int64_t group_k) {
   if (m <= 0 || n <= 0 || k <= 0 || group_k <= 0) return 0;
   SplitPlan pl = quant_plan(kind, m, n, k, seg_len_for(kind, k, group_k));
@@ -539,7 +690,8 @@ extern "C" int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, con
   B2L_REQUIRE(group_size > 0 && k % group_size == 0, "w4a16_matmul: K (%lld) must be a multiple of group_size (%d)",
               (long long)k, group_size);
   B2L_REQUIRE(group_size % 16 == 0, "w4a16_matmul: group_size (%d) must be a multiple of 16", group_size);
-  B2L_REQUIRE(x_row_stride % 8 == 0 && qw_row_stride % 4 == 0, "w4a16_matmul: row strides must be 16-byte multiples");
+  B2L_REQUIRE(x_row_stride % 8 == 0 && qw_row_stride % 4 == 0,
+              "w4a16_matmul: row strides must be 16-byte multiples (K a multiple of 32)");
   if (m == 0) return B2L_OK;
   QuantParams p; SplitPlan pl; CUtensorMap tw, tx;
   int rc = quant_common(Q_INT4, p, pl, y, x, qweight, m, n, k, x_row_stride, qw_row_stride, y_row_stride, workspace,
@@ -559,23 +711,20 @@ extern "C" int b2l_w8a16_matmul(void* y, const void* x, const void* qweight, int
   B2L_REQUIRE(y && x && qweight && scales, "w8a16_matmul: null pointer");
   B2L_REQUIRE(m >= 0 && n > 0 && k > 0 && k % 16 == 0, "w8a16_matmul: K must be a multiple of 16, got %lld", (long long)k);
   B2L_REQUIRE(group_n >= 1 && group_k >= 1, "w8a16_matmul: bad scale block %lldx%lld", (long long)group_n, (long long)group_k);
-  int64_t gk = group_k < k ? group_k : k;
-  // a scale group must contain whole 16-element MMA steps; per-row scales (gk >= K) become one segment
-  if (gk % 16 != 0) gk = k;
   B2L_REQUIRE(group_k >= k || group_k % 16 == 0, "w8a16_matmul: group_k (%lld) must be a multiple of 16 unless it covers K",
               (long long)group_k);
   B2L_REQUIRE(x_row_stride % 8 == 0 && qw_row_stride % 16 == 0, "w8a16_matmul: row strides must be 16-byte multiples");
   if (m == 0) return B2L_OK;
   QuantParams p; SplitPlan pl; CUtensorMap tw, tx;
   const int qk = weight_is_fp8 ? Q_FP8 : Q_INT8;
+  const int seg_len = seg_len_for(qk, k, group_k);
   int rc = quant_common(qk, p, pl, y, x, qweight, m, n, k, x_row_stride, qw_row_stride, y_row_stride, workspace,
-                        workspace_bytes, counters, num_counters, &tw, &tx, "w8a16_matmul", seg_len_for(qk, k, group_k));
+                        workspace_bytes, counters, num_counters, &tw, &tx, "w8a16_matmul", seg_len);
   if (rc != B2L_OK) return rc;
   p.bias = bias; p.bias_is_f32 = bias_is_f32;
   p.scales = (const float*)scales; p.zeros = nullptr; p.s_stride_n = s_row_stride; p.s_stride_k = s_col_stride;
   p.group_n = (int)(group_n > n ? n : group_n);
-  // K must be rounded up to whole 16-steps inside the kernel; scale groups beyond K are never indexed
-  p.group_k = (int)((gk + 15) / 16 * 16);
+  p.group_k = seg_len;
   if (weight_is_fp8) return launch_q<Q_FP8>(tw, tx, p, pl, (cudaStream_t)stream);
   return launch_q<Q_INT8>(tw, tx, p, pl, (cudaStream_t)stream);
 }
