@@ -44,6 +44,8 @@ struct QuantParams {
   const void* bias; int bias_is_f32;
   const float* scales; int64_t s_stride_n, s_stride_k;
   const float* zeros;                      // int4 only (same strides as scales)
+  const void* x; int64_t ldx;              // activations (global): only read by the non-integer zero-point fallback
+  int force_xsum;                          // scale group not a multiple of 64: zero points cannot be folded per sub-block
   int group_n, group_k;                    // int4: group_n = 1, group_k = group_size
   uint32_t* ws; int* counters;
   int M, N, K;
@@ -51,8 +53,10 @@ struct QuantParams {
   int raw_stages;
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
   int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
-  long long* timeline;                     // debug: [8 roles][256] clock64 stamps of CTA (0,0,0), or null
+  long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
+  int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
+enum { DBG_NO_EPI_WAIT = 1, DBG_NO_TMEM_ST = 2, DBG_NO_TMEM_LD = 4, DBG_FORCE_XSUM = 8 };
 
 // role rows of the debug timeline
 enum { TL_PROD = 0, TL_MMA_READY = 1, TL_MMA_ISSUED = 2, TL_DQ_START = 3, TL_DQ_DONE = 4, TL_EPI_START = 5, TL_EPI_DONE = 6 };
@@ -67,7 +71,8 @@ struct __align__(8) QControl {
   uint64_t op_full[kAStages];
   uint64_t op_empty[kAStages];
   uint64_t acc_full[4];
-  int epi_done[4];                         // per epilogue warp: number of segments whose accumulator it has drained
+  uint64_t acc_empty[4];
+  int need_xsum;                           // int4: some zero point of this CTA is not an integer in [0, 1023]
   uint32_t tmem_base;
   int is_last;
 };
@@ -95,12 +100,12 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
   return r;
 }
 // one int32 word (8 nibbles) -> 4 half2 {n0,n1} {n2,n3} {n4,n5} {n6,n7}
-__device__ __forceinline__ void dequant_int4_word(uint32_t w, uint32_t* out) {
+__device__ __forceinline__ void dequant_int4_word(uint32_t w, __half2 add, uint32_t* out) {
   // byte j holds nibbles (2j, 2j+1).  Replicate the byte into both halves, keep nibble 2j in the low
   // half's mantissa and nibble 2j+1 (still shifted left by 4) in the high half's, OR in the fp16
   // exponent of 1024: low = 1024 + n0, high = 1024 + 16*n1; one HFMA2 maps both back to exact integers.
   const __half2 mul = __halves2half2(__float2half(1.0f), __float2half(0.0625f));
-  const __half2 add = __halves2half2(__float2half(-1024.0f), __float2half(-64.0f));
+  // add = {-(1024 + z), -(64 + z)}: an integer zero point z is subtracted in the same (exact) HFMA2
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t rep = __byte_perm(w, w, 0x1111 * j);
@@ -176,6 +181,43 @@ __device__ __forceinline__ void st_release_smem(int* p, int v) {
 // therefore a whole RAW BLOCK (one 128-byte-wide TMA tile: 256 int4 / 128 8-bit K values = 16 / 8 MMAs):
 // the 8 dequant warps fill one TMEM operand stage per raw block, two MMA warps take alternate raw blocks,
 // and "accumulator drained" is a plain shared-memory counter per epilogue warp instead of an mbarrier.
+// Fast issue path of one full raw block whose K range holds NSEG whole segments of SEG_STEPS MMA steps each
+// (scale group divides the raw block).  Everything but the stage addresses is a compile-time constant, so the
+// elected lane runs a straight line of UTCHMMA/UTCBAR; a device timeline showed that ~40 bookkeeping
+// instructions per step in the generic loop cost 160 cycles per MMA against 16 cycles of tensor-pipe time.
+template <int QK, int BT, int SEG_STEPS>
+__device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_base, uint32_t a0, uint64_t bdesc0,
+                                                int seg0, uint64_t* op_empty, uint64_t* raw_empty, int debug) {
+  constexpr int RW = raw_sub<QK>();
+  constexpr int NSEG = RW * 4 / SEG_STEPS;
+  constexpr int NB = 4;
+  constexpr int kXBytes = BT * kStageKBytes;
+  constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
+#pragma unroll
+  for (int s = 0; s < NSEG; ++s) {
+    const int seg = seg0 + s;
+    const int buf = seg & (NB - 1);
+    // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
+    if (!(debug & DBG_NO_EPI_WAIT)) mbar_wait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t d = tmem_base + buf * BT;
+#pragma unroll
+      for (int j = 0; j < SEG_STEPS; ++j) {
+        const int st = s * SEG_STEPS + j;
+        umma_f16_ts(d, a0 + st * 8, bdesc0 + (uint64_t)((((st >> 2) * kXBytes) >> 4) + 2 * (st & 3)), idesc,
+                    j > 0 ? 1u : 0u);
+      }
+      tc_commit(&ctl->acc_full[buf]);
+      if (s == NSEG - 1) {
+        tc_commit(op_empty);
+        tc_commit(raw_empty);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int QK, int BT>
 __global__ void __launch_bounds__(kQuantThreads, 1)
 gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -225,15 +267,18 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < p.raw_stages; ++s) {
       mbar_init(&ctl->raw_full[s], 1);
-      // released by: 8 dequant warps, the MMA warp that owns the block, and (int4) the 4 epilogue warps
-      mbar_init(&ctl->raw_empty[s], 8 + 1 + (QK == Q_INT4 ? 4 : 0));
+      // released by: 8 dequant warps and the MMA warp that owns the block
+      mbar_init(&ctl->raw_empty[s], 8 + 1);
     }
     for (int s = 0; s < NA; ++s) {
       mbar_init(&ctl->op_full[s], 8);
       mbar_init(&ctl->op_empty[s], 1);
     }
-    for (int s = 0; s < NB; ++s) mbar_init(&ctl->acc_full[s], 1);
-    for (int q = 0; q < 4; ++q) ctl->epi_done[q] = 0;
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&ctl->acc_full[s], 1);
+      mbar_init(&ctl->acc_empty[s], 4);
+    }
+    ctl->need_xsum = 0;
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -292,22 +337,26 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           seg_left = seg_steps < steps_here ? seg_steps : steps_here;
           seg_open = false;
         }
-        if (elect_one()) {
-          const uint64_t bdesc0 = x_desc0 + (uint64_t)((rstage * kRawStage) >> 4);
-          const uint32_t a0 = a_base + ostage * kAStageCols;
+        const uint64_t bdesc0 = x_desc0 + (uint64_t)((rstage * kRawStage) >> 4);
+        const uint32_t a0 = a_base + ostage * kAStageCols;
+        if (mma_warps == 2 && steps_here == RW * 4) {
+          // aligned mode: 1 or 2 whole segments per raw block
+          if (seg_steps == RW * 4)
+            issue_raw_block<QK, BT, RW * 4>(ctl, tmem_base, a0, bdesc0, seg, &ctl->op_empty[ostage], &ctl->raw_empty[rstage], p.debug);
+          else
+            issue_raw_block<QK, BT, RW * 2>(ctl, tmem_base, a0, bdesc0, seg, &ctl->op_empty[ostage], &ctl->raw_empty[rstage], p.debug);
+        } else if (elect_one()) {
 #pragma unroll
           for (int st = 0; st < RW * 4; ++st) {
             if (st < steps_here) {
               const int buf = seg % NB;
-              if (!seg_open && seg >= NB) {
-                // accumulator buffer `buf` must have been drained for segment seg-NB by all four epilogue warps
-                const int need = seg - NB + 1;
-                while (ld_acquire_smem(&ctl->epi_done[0]) < need || ld_acquire_smem(&ctl->epi_done[1]) < need ||
-                       ld_acquire_smem(&ctl->epi_done[2]) < need || ld_acquire_smem(&ctl->epi_done[3]) < need) {
-                }
+              if (!seg_open) {
+                // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
+                mbar_wait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1);
                 tc_fence_after();
               }
               const uint64_t bdesc = bdesc0 + (uint64_t)(((st >> 2) * kXBytes) >> 4) + 2 * (st & 3);
+              if (tl && rb < 128) tl[2048 + rb * 16 + st] = clock64();
               umma_f16_ts(tmem_base + buf * BT, a0 + st * 8, bdesc, idesc, seg_open ? 1u : 0u);
               --seg_left;
               if (seg_left == 0) {
@@ -371,9 +420,24 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // every thread reads back only its own row
 
-    // int4: xsum[m] = sum over the segment of x[m, k], computed here from the activation sub-tiles the TMA put
-    // in shared memory (thread -> token m = tid / PARTS, an interleaved share of the segment's 16-byte chunks)
+    // int4: an integer zero point is subtracted exactly by the dequant warps (same HFMA2 that removes the fp16
+    // magic offset), which leaves a scale-only epilogue.  A zero point that is not an integer in [0, 1023]
+    // cannot be folded exactly: then the whole CTA falls back to  acc += s * (P - z * xsum)  with xsum = the
+    // segment's activation row sums (computed here from global memory; rare, correctness path only).
+    bool need_xsum = false;
+    if (QK == Q_INT4) {
+      bool bad = p.force_xsum || (p.debug & DBG_FORCE_XSUM);
+      if (n_ok)
+        for (int g = 0; g < g_count; ++g) {
+          const float z = zero_tab[epi_tid * tab_pitch + g];
+          bad |= !(z >= 0.f && z <= 1023.f && z == rintf(z));
+        }
+      if (bad) atomicOr(&ctl->need_xsum, 1);
+      asm volatile("bar.sync 4, 384;" ::: "memory");        // with the 8 dequant warps: tables + flag are visible
+      need_xsum = ctl->need_xsum != 0;
+    }
     constexpr int PARTS = 128 / BT;
     const int xs_m = epi_tid / PARTS, xs_part = epi_tid % PARTS;
 
@@ -385,30 +449,24 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       int k_next = (k_pos / seg_len + 1) * seg_len;
       if (k_next > k_lim) k_next = k_lim;
       const int g = k_pos / seg_len;
-      float xsum_m = 0.f;
-      if (QK == Q_INT4) {
-        const int c_begin = (k_pos - k_begin) / 8, c_end = (k_next - k_begin) / 8;   // 8-element chunks of the k-range
-        // walk the raw blocks covering this segment one at a time (a segment may be longer than the ring):
-        // wait for the block, add this thread's chunks of it, release it as soon as the k-range is past its end
-        const int rb_lo = (k_pos - k_begin) / kRawK, rb_hi = (k_next - 1 - k_begin) / kRawK;
-        for (int rb = rb_lo; rb <= rb_hi; ++rb) {
-          mbar_wait(&ctl->raw_full[rb % p.raw_stages], (rb / p.raw_stages) & 1);
-          const int lo = c_begin > rb * (kRawK / 8) ? c_begin : rb * (kRawK / 8);
-          const int hi = c_end < (rb + 1) * (kRawK / 8) ? c_end : (rb + 1) * (kRawK / 8);
-          const uint8_t* xbase = raw_ring + (size_t)(rb % p.raw_stages) * kRawStage + kABytes + xs_m * 128;
-          for (int c = lo + xs_part; c < hi; c += PARTS) {
-            const int sub = (c >> 3) % RW, ch = c & 7;               // sub-tile (k-block) and 16-byte chunk of the row
-            const uint4 v = *reinterpret_cast<const uint4*>(xbase + sub * kXBytes + ((ch ^ (xs_m & 7)) << 4));
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
+      if (QK == Q_INT4 && need_xsum) {
+        // thread -> token m = tid / PARTS, an interleaved share of the segment's 8-element chunks
+        float xsum_m = 0.f;
+        const int m = m_tile * BT + xs_m;
+        if (m < p.M) {
+          const __half* xrow = reinterpret_cast<const __half*>(p.x) + (int64_t)m * p.ldx;
+          for (int k = k_pos + xs_part * 8; k < k_next; k += PARTS * 8) {
+            if (k + 8 <= p.K) {
+              const uint4 v = ldg_128(xrow + k);
+              const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = __half22float2(h[q]);
-              xsum_m += f.x + f.y;
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(h[q]);
+                xsum_m += f.x + f.y;
+              }
+            } else {
+              for (int kk = k; kk < p.K; ++kk) xsum_m += __half2float(xrow[kk]);
             }
-          }
-          if (c_end >= (rb + 1) * (kRawK / 8) || k_next == k_lim) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->raw_empty[rb % p.raw_stages]);
           }
         }
 #pragma unroll
@@ -419,40 +477,46 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         asm volatile("bar.sync 3, 128;" ::: "memory");
       }
       const int buf = seg % NB;
-      mbar_wait(&ctl->acc_full[buf], (seg / NB) & 1);
-      tc_fence_after();
-      if (warp == 4) TL_STAMP(TL_EPI_START, seg);
-      if (seg == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");   // own copies only: no barrier needed
       float sc = 0.f, zp = 0.f;
       if (n_ok) {
         sc = scale_tab[epi_tid * tab_pitch + (g - g_first)];
-        if (QK == Q_INT4) zp = zero_tab[epi_tid * tab_pitch + (g - g_first)];
+        if (QK == Q_INT4 && need_xsum) zp = zero_tab[epi_tid * tab_pitch + (g - g_first)];
       }
+      mbar_wait(&ctl->acc_full[buf], (seg / NB) & 1);
+      tc_fence_after();
+      if (warp == 4) TL_STAMP(TL_EPI_START, seg);
       const uint32_t ta = taddr + buf * BT;
+      constexpr int CH = BT < 32 ? BT : 32;                  // columns drained per tcgen05.wait::ld
       const float4* xs4 = reinterpret_cast<const float4*>(xs_smem + (seg & 1) * BT);
 #pragma unroll
-      for (int c = 0; c < BT; c += 16) {
-        uint32_t pv[16];
-        tmem_ld_32x32b_x16(ta + c, pv);
-        tc_wait_ld();
-        if (QK == Q_INT4) {
+      for (int c0 = 0; c0 < BT; c0 += CH) {
+        uint32_t pv[CH];
+        if (!(p.debug & DBG_NO_TMEM_LD)) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 x4 = xs4[(c >> 2) + j4];
-            acc[c + 4 * j4 + 0] = fmaf(sc, fmaf(-zp, x4.x, __uint_as_float(pv[4 * j4 + 0])), acc[c + 4 * j4 + 0]);
-            acc[c + 4 * j4 + 1] = fmaf(sc, fmaf(-zp, x4.y, __uint_as_float(pv[4 * j4 + 1])), acc[c + 4 * j4 + 1]);
-            acc[c + 4 * j4 + 2] = fmaf(sc, fmaf(-zp, x4.z, __uint_as_float(pv[4 * j4 + 2])), acc[c + 4 * j4 + 2]);
-            acc[c + 4 * j4 + 3] = fmaf(sc, fmaf(-zp, x4.w, __uint_as_float(pv[4 * j4 + 3])), acc[c + 4 * j4 + 3]);
+          for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
+          tc_wait_ld();
+        }
+        if (c0 + CH == BT) {
+          // the accumulator is in registers: hand the buffer back before doing the arithmetic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+        }
+        if (QK == Q_INT4 && need_xsum) {
+#pragma unroll
+          for (int j4 = 0; j4 < CH / 4; ++j4) {
+            const float4 x4 = xs4[c0 / 4 + j4];
+            float* a4 = acc + c0 + 4 * j4;
+            a4[0] = fmaf(sc, fmaf(-zp, x4.x, __uint_as_float(pv[4 * j4 + 0])), a4[0]);
+            a4[1] = fmaf(sc, fmaf(-zp, x4.y, __uint_as_float(pv[4 * j4 + 1])), a4[1]);
+            a4[2] = fmaf(sc, fmaf(-zp, x4.z, __uint_as_float(pv[4 * j4 + 2])), a4[2]);
+            a4[3] = fmaf(sc, fmaf(-zp, x4.w, __uint_as_float(pv[4 * j4 + 3])), a4[3]);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c + j]);
+          for (int j = 0; j < CH; ++j) acc[c0 + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c0 + j]);
         }
       }
-      // this warp's quadrant of accumulator buffer `buf` is drained: publish (release) the count
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) st_release_smem(&ctl->epi_done[quad], seg + 1);
       if (warp == 4) TL_STAMP(TL_EPI_DONE, seg);
       k_pos = k_next;
       ++seg;
@@ -497,6 +561,13 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int row = quad * 32 + lane;
     const int rx = row & 7;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    bool fold_zero = false;
+    const int g_first = k_begin / seg_len;
+    const int g_last = (k_begin + steps_total * 16 - 1) / seg_len - g_first;
+    if (QK == Q_INT4) {
+      asm volatile("bar.sync 4, 384;" ::: "memory");        // zero-point table (written by the epilogue threads) + flag
+      fold_zero = ctl->need_xsum == 0;
+    }
     for (int rb = 0; rb < nrb; ++rb) {
       const int rstage = rb % p.raw_stages, ostage = rb % NA;
       mbar_wait(&ctl->raw_full[rstage], (rb / p.raw_stages) & 1);
@@ -513,10 +584,17 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           const uint4 w0 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2) ^ rx) << 4));
           const uint4 w1 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2 + 1) ^ rx) << 4));
           const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float z = 0.f;
+          if (fold_zero) {
+            int g = (k_begin + rb * kRawK + sub * 64) / seg_len - g_first;   // the sub-block lies in one scale group
+            g = g < g_last ? g : g_last;                                     // blocks past K are multiplied by zeros
+            z = zero_tab[row * tab_pitch + g];
+          }
+          const __half2 add = __floats2half2_rn(-1024.f - z, -64.f - z);
           uint32_t vals[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], vals + 4 * j);
-          tmem_st_32x32b_x32(a_stage + sub * 32, vals);
+          for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], add, vals + 4 * j);
+          if (!(p.debug & DBG_NO_TMEM_ST)) tmem_st_32x32b_x32(a_stage + sub * 32, vals);
         }
       } else {
         // 128 raw bytes per row = 2 k-blocks of 64 bytes; this warp: one of them (4 chunks)
@@ -547,6 +625,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 }
 
 static long long* g_timeline = nullptr;   // set through b2l_debug_set_timeline (tools/timeline.py)
+static int g_debug = 0;
 
 constexpr int kMaxGroupsCta = 40;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
 
@@ -629,8 +708,16 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   p.y = y; p.ldy = y_row_stride; p.M = (int)m; p.N = (int)n; p.K = (int)k;
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.num_kb = pl.num_kb; p.raw_stages = pl.stages;
   p.timeline = g_timeline;
-  // two MMA warps on alternate raw blocks are only legal when no segment spans two raw blocks
-  p.aligned = ((qk == Q_INT4 ? 256 : 128) % seg_len == 0);
+  p.debug = g_debug;
+  p.x = x; p.ldx = x_row_stride;
+  p.force_xsum = (qk == Q_INT4 && seg_len % 64 != 0) ? 1 : 0;
+  // Two MMA warps on alternate raw blocks need (a) whole segments inside a raw block and (b) every accumulator
+  // buffer (segment index mod 4) always owned by the same warp, i.e. 1 or 2 segments per raw block: a warp that
+  // waits on an acc_empty phase it did not itself follow could be two phases ahead and alias the parity.
+  {
+    const int raw_k = qk == Q_INT4 ? 256 : 128;
+    p.aligned = (raw_k % seg_len == 0 && raw_k / seg_len <= 2) ? 1 : 0;
+  }
   p.ws = (uint32_t*)workspace; p.counters = (int*)counters;
   if (pl.splits > 1) {
     const int64_t need = (int64_t)pl.n_tiles * pl.m_tiles * pl.splits * pl.bt * kBlockW * 4;
@@ -665,6 +752,10 @@ static inline int seg_len_for(int kind, int64_t k, int64_t group_k) {
 // GEMM launches (null disables).  Not part of the product path.
 extern "C" int b2l_debug_set_timeline(void* device_buffer) {
   gemm::g_timeline = (long long*)device_buffer;
+  return B2L_OK;
+}
+extern "C" int b2l_debug_set_flags(int flags) {
+  gemm::g_debug = flags;
   return B2L_OK;
 }
 

@@ -437,6 +437,21 @@ def test_w4a16_non_integer_zero_points_and_bias():
     close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs, bias), **GEMM_TOL)
 
 
+@pytest.mark.parametrize("m,n,k", [(32, 384, 4096), (7, 130, 1152)])
+def test_w4a16_single_fractional_zero_point_switches_whole_tile(m, n, k):
+    # integer zero points are folded into the operand exactly; one fractional entry anywhere in a tile's rows
+    # must move that tile to the activation-row-sum correction without changing the result
+    gs = 128
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k, dtype=torch.float32) * 0.05
+    qw, sc, zp = ops.quantize_int4_groupwise(w, gs)
+    zp = zp.clone()
+    zp[n // 2, -1] += 0.37
+    zp[0, 0] = 1500.0          # integer but outside the foldable range
+    out = K().w4a16_matmul(x, qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs)
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs), rtol=2e-3, atol=2e-3 + 2e-3 * float(sc.max()) * 1500)
+
+
 def test_w4a16_unpack_order_is_bit_exact():
     # one-hot activations read single weights back: every (n, k) must land on nibble k%8 of word k//8
     n, k, gs = 128, 128, 128

@@ -1,5 +1,5 @@
 """Device timeline of one CTA of the quantised GEMM (debug hook b2l_debug_set_timeline): prints where each
-role spends its cycles per 64-element k-block. Used to find pipeline stalls; not part of the product path."""
+role spends its cycles per raw block (256 int4 / 128 8-bit K values). Used to find pipeline stalls; not part of the product path."""
 
 from __future__ import annotations
 
@@ -21,10 +21,13 @@ def main():
     ap.add_argument("--m", type=int, default=32)
     ap.add_argument("--n", type=int, default=28672)
     ap.add_argument("--k", type=int, default=4096)
+    ap.add_argument("--flags", type=int, default=0)
     a = ap.parse_args()
     lib = _lib.load()
     lib.b2l_debug_set_timeline.argtypes = [ctypes.c_void_p]
     lib.b2l_debug_set_timeline.restype = ctypes.c_int
+    lib.b2l_debug_set_flags.argtypes = [ctypes.c_int]
+    lib.b2l_debug_set_flags.restype = ctypes.c_int
     dev = "cuda"
     x = torch.randn(a.m, a.k, device=dev, dtype=torch.float16) * 0.5
     if a.op == "w4a16":
@@ -39,14 +42,17 @@ def main():
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    tl = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
+    tl = torch.zeros(16 * 256, dtype=torch.int64, device=dev)
+    lib.b2l_debug_set_flags(a.flags)
     lib.b2l_debug_set_timeline(tl.data_ptr())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     flush.zero_()
     fn()
     torch.cuda.synchronize()
     lib.b2l_debug_set_timeline(None)
-    t = tl.cpu().view(8, 256)
+    lib.b2l_debug_set_flags(0)
+    steps = tl.cpu()[2048:].view(128, 16)
+    t = tl.cpu()[:2048].view(8, 256)
     names = ["PROD", "MMA_READY", "MMA_ISSUED", "DQ_START", "DQ_DONE", "EPI_START", "EPI_DONE"]
     t0 = int(t[t > 0].min())
     print(f"total cycles {int(t[t>0].max()) - t0}")
@@ -55,16 +61,21 @@ def main():
         row = [int(v) - t0 for v in t[r][:6] if v > 0]
         print(f"  {nm:10s} {row}")
     rel = lambda r, i: (int(t[r, i]) - t0) if int(t[r, i]) > 0 else -1
-    print("k-block stamps (cycles from first stamp; -1 = not stamped, e.g. k-blocks issued by the second MMA warp):")
-    print("   i  mma_top mma_ready mma_issued | dq_start dq_done")
-    for i in range(0, min(nkb_all := int(max((t[3] > 0).sum(), (t[1] > 0).sum()) * 2), 48)):
-        print(f"  {i:3d} {rel(7,i):7d} {rel(1,i):9d} {rel(2,i):9d} | {rel(3,i):8d} {rel(4,i):8d}")
+    print("raw-block stamps (cycles from first stamp; -1 = not stamped, e.g. blocks issued by the second MMA warp):")
+    print("  rb  prod_issue | mma_top mma_ready mma_issued | dq_start dq_done")
+    for i in range(0, min(int(max((t[3] > 0).sum(), (t[1] > 0).sum()) * 2), 32)):
+        print(f"  {i:3d} {rel(0,i):10d} | {rel(7,i):7d} {rel(1,i):9d} {rel(2,i):9d} | {rel(3,i):8d} {rel(4,i):8d}")
     nseg = int((t[5] > 0).sum())
     print("segment stamps:  s  epi_start epi_done  (dur)")
     for s_ in range(0, min(nseg, 24)):
         print(f"  {s_:3d} {rel(5,s_):9d} {rel(6,s_):9d}  ({rel(6,s_)-rel(5,s_)})")
+    print("per-step issue stamps of raw blocks 6..9 (delta from the block's first step):")
+    for rb in range(6, 10):
+        row = steps[rb]
+        if int(row[0]) > 0:
+            print(f"  rb {rb} first={int(row[0]) - t0}:", [int(v) - int(row[0]) for v in row if v > 0])
     nrb = int((t[0] > 0).sum())
-    print("producer issue times (rb):", [rel(0, i) for i in range(min(nrb, 16))])
+    
 
 
 if __name__ == "__main__":
