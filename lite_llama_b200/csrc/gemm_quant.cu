@@ -45,7 +45,8 @@ struct QuantParams {
   const float* scales; int64_t s_stride_n, s_stride_k;
   const float* zeros;                      // int4 only (same strides as scales)
   const void* x; int64_t ldx;              // activations (global): only read by the non-integer zero-point fallback
-  int force_xsum;                          // scale group not a multiple of 64: zero points cannot be folded per sub-block
+  int force_xsum;                          // scale group is not 64 * 2^n: zero points cannot be folded per sub-block
+  int seg_shift;                           // log2(group_k / 64) when force_xsum == 0
   int group_n, group_k;                    // int4: group_n = 1, group_k = group_size
   uint32_t* ws; int* counters;
   int M, N, K;
@@ -56,7 +57,7 @@ struct QuantParams {
   long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
   int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
-enum { DBG_NO_EPI_WAIT = 1, DBG_NO_TMEM_ST = 2, DBG_NO_TMEM_LD = 4, DBG_FORCE_XSUM = 8 };
+enum { DBG_FORCE_XSUM = 8 };
 
 // role rows of the debug timeline
 enum { TL_PROD = 0, TL_MMA_READY = 1, TL_MMA_ISSUED = 2, TL_DQ_START = 3, TL_DQ_DONE = 4, TL_EPI_START = 5, TL_EPI_DONE = 6 };
@@ -166,6 +167,16 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ float lds_f32(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 __device__ __forceinline__ int ld_acquire_smem(const int* p) {
   int v;
   asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -187,7 +198,7 @@ __device__ __forceinline__ void st_release_smem(int* p, int v) {
 // instructions per step in the generic loop cost 160 cycles per MMA against 16 cycles of tensor-pipe time.
 template <int QK, int BT, int SEG_STEPS>
 __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_base, uint32_t a0, uint64_t bdesc0,
-                                                int seg0, uint64_t* op_empty, uint64_t* raw_empty, int debug) {
+                                                int seg0, uint64_t* op_empty, uint64_t* raw_empty, long long* tl) {
   constexpr int RW = raw_sub<QK>();
   constexpr int NSEG = RW * 4 / SEG_STEPS;
   constexpr int NB = 4;
@@ -198,8 +209,9 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
     const int seg = seg0 + s;
     const int buf = seg & (NB - 1);
     // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
-    if (!(debug & DBG_NO_EPI_WAIT)) mbar_wait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1);
+    mbar_wait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1);
     tc_fence_after();
+    if (tl && seg < 128 && (threadIdx.x & 31) == 0) tl[2048 + seg * 2] = clock64();
     if (elect_one()) {
       const uint32_t d = tmem_base + buf * BT;
 #pragma unroll
@@ -215,6 +227,7 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
       }
     }
     __syncwarp();
+    if (tl && seg < 128 && (threadIdx.x & 31) == 0) tl[2048 + seg * 2 + 1] = clock64();
   }
 }
 
@@ -267,11 +280,11 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < p.raw_stages; ++s) {
       mbar_init(&ctl->raw_full[s], 1);
-      // released by: 8 dequant warps and the MMA warp that owns the block
-      mbar_init(&ctl->raw_empty[s], 8 + 1);
+      // released by: the 4 dequant warps that convert the block and the MMA warp that issues it
+      mbar_init(&ctl->raw_empty[s], 4 + 1);
     }
     for (int s = 0; s < NA; ++s) {
-      mbar_init(&ctl->op_full[s], 8);
+      mbar_init(&ctl->op_full[s], 4);
       mbar_init(&ctl->op_empty[s], 1);
     }
     for (int s = 0; s < NB; ++s) {
@@ -342,9 +355,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (mma_warps == 2 && steps_here == RW * 4) {
           // aligned mode: 1 or 2 whole segments per raw block
           if (seg_steps == RW * 4)
-            issue_raw_block<QK, BT, RW * 4>(ctl, tmem_base, a0, bdesc0, seg, &ctl->op_empty[ostage], &ctl->raw_empty[rstage], p.debug);
+            issue_raw_block<QK, BT, RW * 4>(ctl, tmem_base, a0, bdesc0, seg, &ctl->op_empty[ostage], &ctl->raw_empty[rstage], tl);
           else
-            issue_raw_block<QK, BT, RW * 2>(ctl, tmem_base, a0, bdesc0, seg, &ctl->op_empty[ostage], &ctl->raw_empty[rstage], p.debug);
+            issue_raw_block<QK, BT, RW * 2>(ctl, tmem_base, a0, bdesc0, seg, &ctl->op_empty[ostage], &ctl->raw_empty[rstage], tl);
         } else if (elect_one()) {
 #pragma unroll
           for (int st = 0; st < RW * 4; ++st) {
@@ -445,10 +458,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     int k_pos = k_begin;
     int seg = 0;
     const int k_lim = k_begin + steps_total * 16;
+    int g = g_first;                                   // scale group of the open segment (no division in the loop)
+    int k_group_end = (g_first + 1) * seg_len;
     while (k_pos < k_lim) {
-      int k_next = (k_pos / seg_len + 1) * seg_len;
-      if (k_next > k_lim) k_next = k_lim;
-      const int g = k_pos / seg_len;
+      const int k_next = k_group_end < k_lim ? k_group_end : k_lim;
       if (QK == Q_INT4 && need_xsum) {
         // thread -> token m = tid / PARTS, an interleaved share of the segment's 8-element chunks
         float xsum_m = 0.f;
@@ -479,8 +492,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int buf = seg % NB;
       float sc = 0.f, zp = 0.f;
       if (n_ok) {
-        sc = scale_tab[epi_tid * tab_pitch + (g - g_first)];
-        if (QK == Q_INT4 && need_xsum) zp = zero_tab[epi_tid * tab_pitch + (g - g_first)];
+        sc = lds_f32(scale_tab + epi_tid * tab_pitch + (g - g_first));
+        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + epi_tid * tab_pitch + (g - g_first));
       }
       mbar_wait(&ctl->acc_full[buf], (seg / NB) & 1);
       tc_fence_after();
@@ -491,11 +504,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
       for (int c0 = 0; c0 < BT; c0 += CH) {
         uint32_t pv[CH];
-        if (!(p.debug & DBG_NO_TMEM_LD)) {
 #pragma unroll
-          for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
-          tc_wait_ld();
-        }
+        for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
+        tc_wait_ld();
         if (c0 + CH == BT) {
           // the accumulator is in registers: hand the buffer back before doing the arithmetic
           tc_fence_before();
@@ -519,6 +530,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       if (warp == 4) TL_STAMP(TL_EPI_DONE, seg);
       k_pos = k_next;
+      k_group_end += seg_len;
+      ++g;
       ++seg;
     }
 
@@ -553,9 +566,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
   } else {
-    // ===================== dequant warps 8..15: thread = one weight row, half of each raw block =====================
-    // A warp may only touch the TMEM lane quadrant (warp id % 4).  Warps 8..11 convert the first half of
-    // the raw block's K range, warps 12..15 the second half; all eight arrive on the operand stage's barrier.
+    // ===================== dequant warps 8..15: thread = one weight row of every second raw block =====================
+    // A warp may only touch the TMEM lane quadrant (warp id % 4).  Warps 8..11 convert the even raw blocks,
+    // warps 12..15 the odd ones: the two dequant warps that share a scheduler then sit in different phases
+    // (one waits for its shared-memory loads or its tcgen05.st while the other keeps the ALU pipe busy).
     const int half = (warp - 8) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
@@ -568,45 +582,57 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       asm volatile("bar.sync 4, 384;" ::: "memory");        // zero-point table (written by the epilogue threads) + flag
       fold_zero = ctl->need_xsum == 0;
     }
-    for (int rb = 0; rb < nrb; ++rb) {
+    for (int rb = half; rb < nrb; rb += 2) {
       const int rstage = rb % p.raw_stages, ostage = rb % NA;
-      mbar_wait(&ctl->raw_full[rstage], (rb / p.raw_stages) & 1);
-      mbar_wait(&ctl->op_empty[ostage], ((rb / NA) & 1) ^ 1);
-      tc_fence_after();
-      if (quad == 0 && half == 0) TL_STAMP(TL_DQ_START, rb);
-      const uint8_t* rawrow = raw_ring + (size_t)rstage * kRawStage + row * 128;
-      const uint32_t a_stage = lane_base + kAColBase + ostage * kAStageCols;
+      // zero points of this block's four 64-element sub-blocks (each lies in one scale group); fetched before
+      // the barrier waits so that the table latency is off the conversion's critical path
+      __half2 adds[4];
       if (QK == Q_INT4) {
-        // 128 raw bytes per row = 8 logical 16-byte chunks (swizzled by row & 7) = 4 k-blocks; this warp: 2 of them
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const int sub = half * 2 + s2;
-          const uint4 w0 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2) ^ rx) << 4));
-          const uint4 w1 = *reinterpret_cast<const uint4*>(rawrow + (((sub * 2 + 1) ^ rx) << 4));
-          const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        for (int sub = 0; sub < 4; ++sub) {
           float z = 0.f;
           if (fold_zero) {
-            int g = (k_begin + rb * kRawK + sub * 64) / seg_len - g_first;   // the sub-block lies in one scale group
-            g = g < g_last ? g : g_last;                                     // blocks past K are multiplied by zeros
-            z = zero_tab[row * tab_pitch + g];
+            int g = ((kb0 + rb * 4 + sub) >> p.seg_shift) - g_first;
+            g = g < g_last ? g : g_last;                     // blocks past K are multiplied by zero activations
+            z = lds_f32(zero_tab + row * tab_pitch + g);
           }
-          const __half2 add = __floats2half2_rn(-1024.f - z, -64.f - z);
+          adds[sub] = __floats2half2_rn(-1024.f - z, -64.f - z);
+        }
+      }
+      mbar_wait(&ctl->raw_full[rstage], (rb / p.raw_stages) & 1);
+      const uint8_t* rawrow = raw_ring + (size_t)rstage * kRawStage + row * 128;
+      uint4 raw[8];                                          // the row's 128 raw bytes (8 swizzled 16-byte chunks)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) raw[c] = lds_128(rawrow + ((c ^ rx) << 4));
+      mbar_wait(&ctl->op_empty[ostage], ((rb / NA) & 1) ^ 1);
+      tc_fence_after();
+      if (quad == 0) TL_STAMP(TL_DQ_START, rb);
+      const uint32_t a_stage = lane_base + kAColBase + ostage * kAStageCols;
+      if (QK == Q_INT4) {
+        // 8 chunks = 4 k-blocks of 64 nibbles
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const uint4 w0 = raw[sub * 2], w1 = raw[sub * 2 + 1];
+          const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           uint32_t vals[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], add, vals + 4 * j);
-          if (!(p.debug & DBG_NO_TMEM_ST)) tmem_st_32x32b_x32(a_stage + sub * 32, vals);
+          for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], adds[sub], vals + 4 * j);
+          tmem_st_32x32b_x32(a_stage + sub * 32, vals);
         }
       } else {
-        // 128 raw bytes per row = 2 k-blocks of 64 bytes; this warp: one of them (4 chunks)
-        uint32_t vals[32];
+        // 8 chunks = 2 k-blocks of 64 bytes
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint4 w = *reinterpret_cast<const uint4*>(rawrow + (((half * 4 + c) ^ rx) << 4));
-          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t vals[32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dequant_w8_word(ws[j], QK == Q_FP8, vals + 8 * c + 2 * j);
+          for (int c = 0; c < 4; ++c) {
+            const uint4 w = raw[sub * 4 + c];
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dequant_w8_word(ws[j], QK == Q_FP8, vals + 8 * c + 2 * j);
+          }
+          tmem_st_32x32b_x32(a_stage + sub * 32, vals);
         }
-        tmem_st_32x32b_x32(a_stage + half * 32, vals);
       }
       tc_wait_st();
       tc_fence_before();
@@ -615,7 +641,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_arrive(&ctl->op_full[ostage]);
         mbar_arrive(&ctl->raw_empty[rstage]);     // raw bytes are in registers/TMEM now
       }
-      if (quad == 0 && half == 0) TL_STAMP(TL_DQ_DONE, rb);
+      if (quad == 0) TL_STAMP(TL_DQ_DONE, rb);
     }
   }
 
@@ -710,7 +736,12 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   p.timeline = g_timeline;
   p.debug = g_debug;
   p.x = x; p.ldx = x_row_stride;
-  p.force_xsum = (qk == Q_INT4 && seg_len % 64 != 0) ? 1 : 0;
+  p.force_xsum = 0; p.seg_shift = 0;
+  if (qk == Q_INT4) {
+    const int q64 = seg_len / 64;
+    if (seg_len % 64 != 0 || (q64 & (q64 - 1)) != 0) p.force_xsum = 1;
+    else while ((1 << p.seg_shift) < q64) ++p.seg_shift;
+  }
   // Two MMA warps on alternate raw blocks need (a) whole segments inside a raw block and (b) every accumulator
   // buffer (segment index mod 4) always owned by the same warp, i.e. 1 or 2 segments per raw block: a warp that
   // waits on an acc_empty phase it did not itself follow could be two phases ahead and alias the parity.

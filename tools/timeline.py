@@ -69,11 +69,12 @@ def main():
     print("segment stamps:  s  epi_start epi_done  (dur)")
     for s_ in range(0, min(nseg, 24)):
         print(f"  {s_:3d} {rel(5,s_):9d} {rel(6,s_):9d}  ({rel(6,s_)-rel(5,s_)})")
-    print("per-step issue stamps of raw blocks 6..9 (delta from the block's first step):")
-    for rb in range(6, 10):
-        row = steps[rb]
-        if int(row[0]) > 0:
-            print(f"  rb {rb} first={int(row[0]) - t0}:", [int(v) - int(row[0]) for v in row if v > 0])
+    print("MMA fast path per segment: acc_empty wait done -> issue done (cycles from first stamp)")
+    flat = steps.reshape(-1)
+    for sg in range(8, 20):
+        a0, a1 = int(flat[2 * sg]), int(flat[2 * sg + 1])
+        if a0 > 0:
+            print(f"  seg {sg}: {a0 - t0} -> {a1 - t0}  ({a1 - a0})")
     nrb = int((t[0] > 0).sum())
     
 
