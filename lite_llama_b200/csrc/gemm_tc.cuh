@@ -35,6 +35,7 @@ struct SplitPlan {
   int splits;
   int kb_per_split;
   int stages;
+  int x_stages;       // quantised GEMMs: depth of the separate activation ring
   int smem_bytes;
 };
 
