@@ -50,6 +50,10 @@ int b2l_version(void);
 int b2l_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
 /* number of kernels this library has launched in this process (monotonic; bench.py's gpu_launches) */
 int64_t b2l_launch_count(void);
+/* Programmatic dependent launch (every kernel is launched so that the next one's set-up and weight prefetch
+ * overlap it; see csrc/common.cuh).  Returns the previous setting.  Also: environment B2L_PDL=0 at load.
+ * No reference counterpart: the reference launches every Triton kernel fully serialised. */
+int b2l_set_pdl(int enabled);
 
 /* skip_rmsnorm(X, residual, weight, eps) -- lite_llama/kernels/skip_rmsnorm.py:192-234.
  * residual (nullable) is updated in place with x + residual (rounded to dtype); y gets

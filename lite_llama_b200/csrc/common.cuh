@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 
 // --------------------------------------------------------------------------- //
 // Error plumbing (thread-local last-error string, negative return codes)
@@ -62,6 +63,7 @@ void b2l_count_launch();
 #define B2L_F16 0
 #define B2L_BF16 1
 
+int b2l_pdl_enabled();        // programmatic dependent launch switch (b2l_set_pdl / env B2L_PDL; default on)
 int b2l_num_sms();            // cached cudaDevAttrMultiProcessorCount of the current device
 int b2l_max_smem_optin();     // cached cudaDevAttrMaxSharedMemoryPerBlockOptin
 
@@ -342,9 +344,41 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, f
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Programmatic dependent launch: let the next kernel's prologue overlap our tail,
-// and wait for the previous kernel's memory before touching its outputs.
+// Programmatic dependent launch (PDL).  A decode step is ~350 kernels of 2-40 us each, so the launch gap
+// between two kernels (grid drain + launch latency, ~2 us even inside a CUDA graph) is a quarter of the step.
+// Every kernel of this library is launched with the "programmatic stream serialization" attribute and
+//   * calls pdl_launch_dependents() first thing, so the NEXT kernel is launched while this one runs: its CTAs
+//     become resident wherever an SM has room, set up barriers/TMEM and -- the GEMMs -- start streaming
+//     their (static) weights;
+//   * calls pdl_wait_prior() before its first access to anything an earlier kernel may have written, or to
+//     anything it writes itself that an earlier kernel may still read.  The wait returns when the previous
+//     kernel has completed and flushed; since that kernel waited for ITS predecessor before finishing,
+//     completion is transitive over the whole stream.  Every kernel must therefore execute the wait on
+//     every path.  Without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// for kernels whose first instruction already reads the previous kernel's output
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait_prior();
+}
+
+// Host side: launch `kern` on `st`, with the PDL attribute unless the library switch is off.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b2l_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = b2l_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 #endif  // __CUDACC__

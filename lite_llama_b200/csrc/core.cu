@@ -16,6 +16,23 @@ static std::atomic<long long> g_launches{0};
 void b2l_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" int64_t b2l_launch_count(void) { return (int64_t)g_launches.load(); }
 
+// Programmatic dependent launch switch: env B2L_PDL=0 disables it at load, b2l_set_pdl() at run time
+// (tests compare both modes; a captured CUDA graph keeps the mode it was captured with).
+#include <stdlib.h>
+static int g_pdl = -1;
+int b2l_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("B2L_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
+extern "C" int b2l_set_pdl(int enabled) {
+  const int old = b2l_pdl_enabled();
+  g_pdl = enabled ? 1 : 0;
+  return old;
+}
+
 extern "C" const char* b2l_last_error(void) { return g_err; }
 extern "C" int b2l_version(void) { return 100; }
 

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) skip_rmsnorm_block_kernel(T* __restrict__
                                                                  T* __restrict__ res, const T* __restrict__ w,
                                                                  int64_t n, int64_t x_stride, int64_t r_stride,
                                                                  int64_t y_stride, float eps) {
+  pdl_prologue();
   // One CTA per row; each thread keeps up to VPT_MAX 16-byte chunks in registers.
   const int64_t row = blockIdx.x;
   const T* xr = x + row * x_stride;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) skip_rmsnorm_block_kernel(T* __restrict__
 template <typename T>
 __global__ void skip_rmsnorm_warp_kernel(T* __restrict__ y, const T* __restrict__ x, const T* __restrict__ w,
                                          int64_t rows, int64_t n, int64_t x_stride, int64_t y_stride, float eps) {
+  pdl_prologue();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -122,6 +124,7 @@ template <typename T, int KEEP>
 __global__ void skip_rmsnorm_warp_reg_kernel(T* __restrict__ y, const T* __restrict__ x, T* __restrict__ res,
                                              const T* __restrict__ w, int64_t rows, int64_t n, int64_t x_stride,
                                              int64_t r_stride, int64_t y_stride, float eps) {
+  pdl_prologue();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -171,31 +174,31 @@ static int launch_skip_rmsnorm(void* y, const void* x, void* res, const void* w,
     int vpt = (int)cdiv64(chunks, threads);
     T* yy = (T*)y; const T* xx = (const T*)x; T* rr = (T*)res; const T* ww = (const T*)w;
     if (vpt <= 1)
-      skip_rmsnorm_block_kernel<T, 1><<<(unsigned)rows, threads, 0, st>>>(yy, xx, rr, ww, n, xs, rs, ys, eps);
+      b2l_launch(skip_rmsnorm_block_kernel<T, 1>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, yy, xx, rr, ww, n, xs, rs, ys, eps);
     else if (vpt <= 2)
-      skip_rmsnorm_block_kernel<T, 2><<<(unsigned)rows, threads, 0, st>>>(yy, xx, rr, ww, n, xs, rs, ys, eps);
+      b2l_launch(skip_rmsnorm_block_kernel<T, 2>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, yy, xx, rr, ww, n, xs, rs, ys, eps);
     else if (vpt <= 4)
-      skip_rmsnorm_block_kernel<T, 4><<<(unsigned)rows, threads, 0, st>>>(yy, xx, rr, ww, n, xs, rs, ys, eps);
+      b2l_launch(skip_rmsnorm_block_kernel<T, 4>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, yy, xx, rr, ww, n, xs, rs, ys, eps);
     else
-      skip_rmsnorm_block_kernel<T, 8><<<(unsigned)rows, threads, 0, st>>>(yy, xx, rr, ww, n, xs, rs, ys, eps);
+      b2l_launch(skip_rmsnorm_block_kernel<T, 8>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, yy, xx, rr, ww, n, xs, rs, ys, eps);
     B2L_LAUNCH_CHECK();
     return B2L_OK;
   }
   const int warps = 4;
   const unsigned grid = (unsigned)cdiv64(rows, warps);
   if (n <= 32 * 4)
-    skip_rmsnorm_warp_reg_kernel<T, 4><<<grid, warps * 32, 0, st>>>((T*)y, (const T*)x, (T*)res, (const T*)w, rows, n,
+    b2l_launch(skip_rmsnorm_warp_reg_kernel<T, 4>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (T*)res, (const T*)w, rows, n,
                                                                  xs, rs, ys, eps);
   else if (n <= 32 * 32)
-    skip_rmsnorm_warp_reg_kernel<T, 32><<<grid, warps * 32, 0, st>>>((T*)y, (const T*)x, (T*)res, (const T*)w, rows,
+    b2l_launch(skip_rmsnorm_warp_reg_kernel<T, 32>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (T*)res, (const T*)w, rows,
                                                                   n, xs, rs, ys, eps);
   else if (n <= 32 * 128)
-    skip_rmsnorm_warp_reg_kernel<T, 128><<<grid, warps * 32, 0, st>>>((T*)y, (const T*)x, (T*)res, (const T*)w, rows,
+    b2l_launch(skip_rmsnorm_warp_reg_kernel<T, 128>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (T*)res, (const T*)w, rows,
                                                                    n, xs, rs, ys, eps);
   else {
     B2L_REQUIRE(res == nullptr, "skip_rmsnorm: unaligned rows wider than 4096 with a residual are unsupported (n=%lld)",
                 (long long)n);
-    skip_rmsnorm_warp_kernel<T><<<grid, warps * 32, 0, st>>>((T*)y, (const T*)x, (const T*)w, rows, n, xs, ys, eps);
+    b2l_launch(skip_rmsnorm_warp_kernel<T>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (const T*)w, rows, n, xs, ys, eps);
   }
   B2L_LAUNCH_CHECK();
   return B2L_OK;
@@ -243,6 +246,7 @@ __global__ void rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __res
                             const T* __restrict__ sinp, int seq_len, int n_qh, int n_kh, int hd, int64_t q_tok_stride,
                             int64_t q_head_stride, int64_t k_tok_stride, int64_t k_head_stride, int64_t cs_b_stride,
                             int64_t cs_s_stride) {
+  pdl_prologue();
   using T2 = typename Vec2<T>::type;
   const int64_t tok = blockIdx.x;
   const int64_t b = tok / seq_len, s = tok % seq_len;
@@ -272,6 +276,7 @@ __global__ void rope_kernel_scalar(T* __restrict__ q, T* __restrict__ k, const T
                                    const T* __restrict__ sinp, int seq_len, int n_qh, int n_kh, int hd,
                                    int64_t q_tok_stride, int64_t q_head_stride, int64_t k_tok_stride,
                                    int64_t k_head_stride, int64_t cs_b_stride, int64_t cs_s_stride) {
+  pdl_prologue();
   const int64_t tok = blockIdx.x;
   const int64_t b = tok / seq_len, s = tok % seq_len;
   const T* cr = cosp + b * cs_b_stride + s * cs_s_stride;
@@ -309,17 +314,17 @@ extern "C" int b2l_rope_emb(void* q, void* k, const void* cos, const void* sin, 
                   cs_batch_stride, cs_seq_stride
   if (dtype == B2L_F16) {
     if (vec)
-      rope_kernel<__half><<<(unsigned)tokens, threads, 0, st>>>((__half*)q, (__half*)k, (const __half*)cos,
+      b2l_launch(rope_kernel<__half>, dim3((unsigned)tokens), dim3(threads), (size_t)(0), st, (__half*)q, (__half*)k, (const __half*)cos,
                                                                (const __half*)sin, ROPE_ARGS);
     else
-      rope_kernel_scalar<__half><<<(unsigned)tokens, threads, 0, st>>>((__half*)q, (__half*)k, (const __half*)cos,
+      b2l_launch(rope_kernel_scalar<__half>, dim3((unsigned)tokens), dim3(threads), (size_t)(0), st, (__half*)q, (__half*)k, (const __half*)cos,
                                                                       (const __half*)sin, ROPE_ARGS);
   } else if (dtype == B2L_BF16) {
     if (vec)
-      rope_kernel<__nv_bfloat16><<<(unsigned)tokens, threads, 0, st>>>(
+      b2l_launch(rope_kernel<__nv_bfloat16>, dim3((unsigned)tokens), dim3(threads), (size_t)(0), st, 
           (__nv_bfloat16*)q, (__nv_bfloat16*)k, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, ROPE_ARGS);
     else
-      rope_kernel_scalar<__nv_bfloat16><<<(unsigned)tokens, threads, 0, st>>>(
+      b2l_launch(rope_kernel_scalar<__nv_bfloat16>, dim3((unsigned)tokens), dim3(threads), (size_t)(0), st, 
           (__nv_bfloat16*)q, (__nv_bfloat16*)k, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, ROPE_ARGS);
   } else {
     B2L_UNSUPPORTED("rope_emb: dtype %d", dtype);
@@ -344,6 +349,7 @@ __device__ __forceinline__ float silu_f32(float x) {
 template <typename T>
 __global__ void swiglu_kernel(T* __restrict__ c, const T* __restrict__ a, const T* __restrict__ b, int64_t rows,
                               int64_t n, int64_t a_stride, int64_t b_stride, int64_t c_stride, int vec) {
+  pdl_prologue();
   // grid.y = rows (grid-stride), grid.x * blockDim.x sweeps the row in 8-element chunks
   for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
     const T* ar = a + row * a_stride;
@@ -383,10 +389,10 @@ extern "C" int b2l_swiglu(void* c, const void* a, const void* b, int64_t rows, i
   unsigned gy = (unsigned)(rows > 65535 ? 65535 : rows);
   dim3 grid(gx, gy);
   if (dtype == B2L_F16)
-    swiglu_kernel<__half><<<grid, threads, 0, st>>>((__half*)c, (const __half*)a, (const __half*)b, rows, n,
+    b2l_launch(swiglu_kernel<__half>, dim3(grid), dim3(threads), (size_t)(0), st, (__half*)c, (const __half*)a, (const __half*)b, rows, n,
                                                    a_row_stride, b_row_stride, c_row_stride, vec);
   else if (dtype == B2L_BF16)
-    swiglu_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>((__nv_bfloat16*)c, (const __nv_bfloat16*)a,
+    b2l_launch(swiglu_kernel<__nv_bfloat16>, dim3(grid), dim3(threads), (size_t)(0), st, (__nv_bfloat16*)c, (const __nv_bfloat16*)a,
                                                           (const __nv_bfloat16*)b, rows, n, a_row_stride, b_row_stride,
                                                           c_row_stride, vec);
   else
@@ -406,6 +412,7 @@ __global__ void update_kv_buffer_kernel(const char* __restrict__ src_a, const ch
                                         int heads_a, int heads_total, int row_bytes, int64_t a_tok_stride,
                                         int64_t a_head_stride, int64_t b_tok_stride, int64_t b_head_stride,
                                         int64_t d_tok_stride, int64_t d_head_stride, int vec) {
+  pdl_prologue();
   const int64_t t = blockIdx.x;
   const int64_t dest = load_index(select_index, t, idx_width);
   const int per_head = vec ? row_bytes / 16 : row_bytes / 2;
@@ -441,7 +448,7 @@ extern "C" int b2l_update_kv_buffer(const void* src_a, const void* src_b, const 
   const int heads = heads_a + heads_b;
   const int work = heads * (vec ? row_bytes / 16 : row_bytes / 2);
   const int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
-  update_kv_buffer_kernel<<<(unsigned)tokens, threads, 0, (cudaStream_t)stream>>>(
+  b2l_launch(update_kv_buffer_kernel, dim3((unsigned)tokens), dim3(threads), (size_t)(0), (cudaStream_t)stream, 
       (const char*)src_a, (const char*)src_b, select_index, index_width, (char*)kv_buffer, heads_a, heads, row_bytes,
       a_tok_stride * 2, a_head_stride * 2, b_tok_stride * 2, b_head_stride * 2, d_tok_stride * 2, d_head_stride * 2,
       vec);
@@ -456,6 +463,7 @@ extern "C" int b2l_update_kv_buffer(const void* src_a, const void* src_b, const 
 __global__ void update_kv_index_kernel(int32_t* __restrict__ table, const void* __restrict__ req_idx, int req_w,
                                        const void* __restrict__ seq_len, int len_w, const void* __restrict__ sel,
                                        int sel_w, int64_t n, int64_t stride_b, int64_t stride_s) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t r = load_index(req_idx, i, req_w);
@@ -470,7 +478,7 @@ extern "C" int b2l_update_kv_index(void* table, const void* b_req_idx, int req_w
   B2L_REQUIRE((req_width == 4 || req_width == 8) && (len_width == 4 || len_width == 8) &&
                   (sel_width == 4 || sel_width == 8), "update_kv_index: index widths must be 4 or 8");
   if (n == 0) return B2L_OK;
-  update_kv_index_kernel<<<(unsigned)cdiv64(n, 128), 128, 0, (cudaStream_t)stream>>>(
+  b2l_launch(update_kv_index_kernel, dim3((unsigned)cdiv64(n, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, 
       (int32_t*)table, b_req_idx, req_width, b_seq_len, len_width, select_index, sel_width, n, stride_b, stride_s);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
@@ -486,6 +494,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) quantize_act_int8_kernel(int8_t* __restrict__ q, float* __restrict__ scales,
                                                                 const T* __restrict__ x, int64_t k, int64_t x_stride,
                                                                 int64_t q_stride) {
+  pdl_prologue();
   const int64_t row = blockIdx.x;
   const T* xr = x + row * x_stride;
   int8_t* qr = q + row * q_stride;
@@ -516,10 +525,10 @@ extern "C" int b2l_quantize_activations_int8(void* q, void* scales, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = k >= 2048 ? 256 : 128;
   if (dtype == B2L_F16)
-    quantize_act_int8_kernel<__half><<<(unsigned)m, threads, 0, st>>>((int8_t*)q, (float*)scales, (const __half*)x, k,
+    b2l_launch(quantize_act_int8_kernel<__half>, dim3((unsigned)m), dim3(threads), (size_t)(0), st, (int8_t*)q, (float*)scales, (const __half*)x, k,
                                                                      x_row_stride, q_row_stride);
   else if (dtype == B2L_BF16)
-    quantize_act_int8_kernel<__nv_bfloat16><<<(unsigned)m, threads, 0, st>>>(
+    b2l_launch(quantize_act_int8_kernel<__nv_bfloat16>, dim3((unsigned)m), dim3(threads), (size_t)(0), st, 
         (int8_t*)q, (float*)scales, (const __nv_bfloat16*)x, k, x_row_stride, q_row_stride);
   else
     B2L_UNSUPPORTED("quantize_activations_int8: dtype %d", dtype);
@@ -533,6 +542,7 @@ extern "C" int b2l_quantize_activations_int8(void* q, void* scales, const void* 
 // --------------------------------------------------------------------------- //
 template <typename T>
 __global__ void moe_sum_kernel(T* __restrict__ out, const T* __restrict__ in, int64_t n, int top_k) {
+  pdl_prologue();
   const int64_t m = blockIdx.y;
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
@@ -548,9 +558,9 @@ extern "C" int b2l_moe_sum(void* out, const void* in, int64_t tokens, int64_t n,
   dim3 grid((unsigned)cdiv64(n, 256), (unsigned)tokens);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2L_F16)
-    moe_sum_kernel<__half><<<grid, 256, 0, st>>>((__half*)out, (const __half*)in, n, top_k);
+    b2l_launch(moe_sum_kernel<__half>, dim3(grid), dim3(256), (size_t)(0), st, (__half*)out, (const __half*)in, n, top_k);
   else if (dtype == B2L_BF16)
-    moe_sum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)out, (const __nv_bfloat16*)in, n, top_k);
+    b2l_launch(moe_sum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), st, (__nv_bfloat16*)out, (const __nv_bfloat16*)in, n, top_k);
   else
     B2L_UNSUPPORTED("moe_sum: dtype %d", dtype);
   B2L_LAUNCH_CHECK();

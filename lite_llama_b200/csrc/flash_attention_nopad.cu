@@ -39,6 +39,7 @@ template <int D> __host__ __device__ constexpr int smem_bytes() { return kStages
 
 template <typename T, int D>
 __global__ void __launch_bounds__(kThreads) flash_prefill_kernel(const PrefillParams p) {
+  pdl_prologue();   // everything below reads what earlier kernels of the step wrote (q, KV rows, lengths, table)
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kStages;
@@ -233,7 +234,7 @@ int launch_prefill(const PrefillParams& p, int64_t batch, int64_t max_len, cudaS
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv64(max_len, kBM), (unsigned)p.Hq, (unsigned)batch);
-  flash_prefill_kernel<T, D><<<grid, kThreads, smem, st>>>(p);
+  b2l_launch(flash_prefill_kernel<T, D>, dim3(grid), dim3(kThreads), (size_t)(smem), st, p);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
 }

@@ -51,6 +51,7 @@ __host__ __device__ inline int row_pitch(int HB, int D) { return 2 * HB * D * 2 
 
 template <typename T, int D>
 __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) flash_decode_split_kernel(const DecodeParams p) {
+  pdl_prologue();   // everything below reads what earlier kernels of the step wrote (q, KV rows, lengths, table)
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;              // [kMaxStages]
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) flash_decode_split_k
 // Stage 2: log-sum-exp merge of the per-split partials (reference: flashdecoding.py:224-313).
 template <typename T, int D>
 __global__ void flash_decode_combine_kernel(const DecodeParams p) {
+  pdl_prologue();
   const int b = blockIdx.x, head = blockIdx.y;
   const int64_t seq_len = load_index(p.seq_len, b, p.len_w);
   int nsp = (int)((seq_len + p.chunk - 1) / p.chunk);
@@ -325,11 +327,11 @@ int launch_decode(const DecodeParams& p, const Plan& pl, int64_t batch, cudaStre
   }
   dim3 grid((unsigned)p.splits, (unsigned)(p.Hkv / p.HB), (unsigned)batch);
   const int threads = (p.HB * p.qblocks + 1) * 32;
-  flash_decode_split_kernel<T, D><<<grid, threads, pl.smem, st>>>(p);
+  b2l_launch(flash_decode_split_kernel<T, D>, dim3(grid), dim3(threads), (size_t)(pl.smem), st, p);
   B2L_LAUNCH_CHECK();
   if (p.splits > 1) {
     dim3 g2((unsigned)batch, (unsigned)p.Hq);
-    flash_decode_combine_kernel<T, D><<<g2, D >= 128 ? 128 : 64, 0, st>>>(p);
+    b2l_launch(flash_decode_combine_kernel<T, D>, dim3(g2), dim3(D >= 128 ? 128 : 64), (size_t)(0), st, p);
     B2L_LAUNCH_CHECK();
   }
   return B2L_OK;

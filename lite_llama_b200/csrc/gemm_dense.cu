@@ -38,6 +38,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int kb0 = split * p.kb_per_split;
   const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
   const int nkb = kb1 - kb0;
+  pdl_launch_dependents();   // the next kernel may set itself up while this one streams weights (common.cuh)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -60,8 +61,27 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    // Weights are static, activations are the previous kernel's output: under programmatic dependent launch
+    // the first ring-full of weight tiles is requested BEFORE waiting for the previous kernel to finish.
+    const int pre = nkb < p.stages ? nkb : p.stages;
+    if (elect_one()) {
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&ctl->full[i], kABytes + kBBytes);
+        tma_load_2d_hint(a_ring + (size_t)i * kABytes, &tmap_w, (kb0 + i) * kKPerStage, n_tile * kBlockW, &ctl->full[i],
+                         kEvictFirst);
+      }
+    }
+    __syncwarp();
+    pdl_wait_prior();
+    if (elect_one()) {
+      for (int i = 0; i < pre; ++i)
+        tma_load_2d_hint(b_ring + (size_t)i * kBBytes, &tmap_x, (kb0 + i) * kKPerStage, m_tile * BT, &ctl->full[i],
+                         kEvictLast);
+    }
+    __syncwarp();
     PipeState ps(p.stages);
-    for (int i = 0; i < nkb; ++i) {
+    for (int i = 0; i < pre; ++i) ps.advance();
+    for (int i = pre; i < nkb; ++i) {
       mbar_wait(&ctl->empty[ps.stage], ps.phase ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&ctl->full[ps.stage], kABytes + kBBytes);
@@ -112,6 +132,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int tile_id = m_tile * gridDim.x + n_tile;
     mbar_wait(&ctl->acc_full[0], 0);
     tc_fence_after();
+    pdl_wait_prior();   // activation scales are upstream data; y / the split-K workspace may still be read upstream
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     constexpr int CH = 16;
     T* y = reinterpret_cast<T*>(p.y);
@@ -193,7 +214,7 @@ static int launch_bt(const CUtensorMap& tw, const CUtensorMap& tx, const DensePa
     configured_smem = pl.smem_bytes;
   }
   dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.m_tiles, (unsigned)pl.splits);
-  kern<<<grid, 192, pl.smem_bytes, st>>>(tw, tx, p);
+  b2l_launch(kern, dim3(grid), dim3(192), (size_t)(pl.smem_bytes), st, tw, tx, p);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
 }

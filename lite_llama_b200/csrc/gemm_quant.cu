@@ -58,13 +58,13 @@ struct QuantParams {
   int M, N, K;
   int splits, kb_per_split, num_kb;
   int w_stages, x_stages;                  // ring depths: raw weight blocks / activation blocks
-  int pdl;                                 // launched with programmatic stream serialisation (griddepcontrol.wait needed)
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
   int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
   long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
   int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
 enum { DBG_FORCE_XSUM = 8 };
+constexpr int kTlMisc = 3072;   // timeline: start-up / shutdown stamps of CTA (0,0,0), see tools/timeline.py
 
 // role rows of the debug timeline
 enum { TL_PROD = 0, TL_MMA_READY = 1, TL_MMA_ISSUED = 2, TL_DQ_START = 3, TL_DQ_DONE = 4, TL_EPI_START = 5, TL_EPI_DONE = 6 };
@@ -290,6 +290,46 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   // two MMA warps (alternate raw blocks) when no segment spans two raw blocks, else warp 1 alone
   const int mma_warps = p.aligned ? 2 : 1;
 
+  pdl_launch_dependents();   // the next kernel may set itself up while this one streams weights (common.cuh)
+  if (tl && threadIdx.x == 0) tl[kTlMisc + 0] = clock64();
+
+  if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
+    // Stage this CTA's scale / zero-point rows FIRST: the dequant warps cannot convert a single weight before the
+    // zero points are here, and a request issued after the weight ring's TMA loads queues behind 128 KiB per SM
+    // of weight traffic (ncu: the dequant warps spent a quarter of the CTA's life at the start-up barrier).
+    // Each epilogue thread copies -- and later reads back -- only its own row, so no barrier is involved;
+    // 16 bytes (4 groups) per cp.async when the row is contiguous and aligned.  The tables are weights (static),
+    // so this runs before griddepcontrol.wait.
+    const int epi_tid = (warp & 3) * 32 + lane;
+    const int n = n_tile * kBlockW + epi_tid;
+    const int g_first = k_begin / seg_len;
+    const int g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+    if (n < p.N) {
+      const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g_first * p.s_stride_k;
+      const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n + (int64_t)g_first * p.s_stride_k : nullptr;
+      float* sdst = scale_tab + epi_tid * tab_pitch;
+      float* zdst = zero_tab + epi_tid * tab_pitch;
+      const bool vec = p.s_stride_k == 1 && ((uintptr_t)srow % 16 == 0) && (QK != Q_INT4 || (uintptr_t)zrow % 16 == 0);
+      int g = 0;
+      if (vec) {
+        // zero points first: they gate the dequant warps, the scales are only needed by the first drain
+        if (QK == Q_INT4)
+          for (int gz = 0; gz + 4 <= g_count; gz += 4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(zdst + gz)), "l"(zrow + gz) : "memory");
+        for (; g + 4 <= g_count; g += 4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + g)), "l"(srow + g) : "memory");
+      }
+      for (; g < g_count; ++g) {
+        if (QK == Q_INT4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zdst + g)),
+                       "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst + g)),
+                     "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
   if (warp == kWarpWProd && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
@@ -320,6 +360,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (tl && threadIdx.x == 0) tl[kTlMisc + 1] = clock64();
 
   if (warp == kWarpWProd) {
     // ===================== weight producer (whole warp loops, one elected lane issues) =====================
@@ -340,7 +381,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
   } else if (warp == kWarpXProd) {
     // ===================== activation producer =====================
-    if (p.pdl) pdl_wait_prior();             // the activations are the previous kernel's output
+    pdl_wait_prior();                        // the activations are the previous kernel's output
     PipeState xs(p.x_stages);
     for (int rb = 0; rb < nrb; ++rb) {
       mbar_wait(&ctl->x_empty[xs.stage], xs.phase ^ 1);
@@ -439,35 +480,11 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
     for (int j = 0; j < BT; ++j) acc[j] = 0.f;
 
-    // stage this row's scales / zero points for every group of the CTA's k-range with cp.async (a per-segment
-    // global load would put a DRAM round trip on the drain's critical path); 16 bytes (4 groups) per copy when
-    // the row is contiguous and aligned.  The wait is deferred until the first accumulator is ready.
+    // this row's scales / zero points were requested at kernel entry (see above); wait for them here
     const int g_first = k_begin / seg_len;
     const int g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
-    if (n_ok) {
-      const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g_first * p.s_stride_k;
-      const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n + (int64_t)g_first * p.s_stride_k : nullptr;
-      float* sdst = scale_tab + epi_tid * tab_pitch;
-      float* zdst = zero_tab + epi_tid * tab_pitch;
-      const bool vec = p.s_stride_k == 1 && ((uintptr_t)srow % 16 == 0) && (QK != Q_INT4 || (uintptr_t)zrow % 16 == 0);
-      int g = 0;
-      if (vec) {
-        for (; g + 4 <= g_count; g += 4) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + g)), "l"(srow + g) : "memory");
-          if (QK == Q_INT4)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(zdst + g)), "l"(zrow + g) : "memory");
-        }
-      }
-      for (; g < g_count; ++g) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst + g)),
-                     "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
-        if (QK == Q_INT4)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zdst + g)),
-                       "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // every thread reads back only its own row
+    if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 2] = clock64();
 
     // int4: an integer zero point is subtracted exactly by the dequant warps (same HFMA2 that removes the fp16
     // magic offset), which leaves a scale-only epilogue.  A zero point that is not an integer in [0, 1023]
@@ -484,7 +501,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (bad) atomicOr(&ctl->need_xsum, 1);
       asm volatile("bar.sync 4, 384;" ::: "memory");        // with the 8 dequant warps: tables + flag are visible
       need_xsum = ctl->need_xsum != 0;
+      if (need_xsum) pdl_wait_prior();   // the fallback reads the activations (the previous kernel's output) from global
     }
+    if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 3] = clock64();
     constexpr int PARTS = 128 / BT;
     const int xs_m = epi_tid / PARTS, xs_part = epi_tid % PARTS;
 
@@ -569,7 +588,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       ++seg;
     }
 
-    if (p.pdl) pdl_wait_prior();     // output / workspace buffers may still be in use by the previous kernel
+    if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 5] = clock64();
+    pdl_wait_prior();                // output / workspace buffers may still be in use by the previous kernel
     T* y = reinterpret_cast<T*>(p.y);
     auto store_final = [&]() {
       if (!n_ok) return;
@@ -618,6 +638,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       asm volatile("bar.sync 4, 384;" ::: "memory");        // zero-point table (written by the epilogue threads) + flag
       fold_zero = ctl->need_xsum == 0;
     }
+    if (tl && warp == 0 && lane == 0) tl[kTlMisc + 4] = clock64();
     for (int rb = half; rb < nrb; rb += 2) {
       const int rstage = rb % p.w_stages;
       // zero points of this block's four 64-element sub-blocks (each lies in one scale group); fetched before
@@ -691,6 +712,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (tl && threadIdx.x == 0) tl[kTlMisc + 6] = clock64();
   if (warp == kWarpMma0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -770,7 +792,7 @@ static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const Quant
     configured_smem = pl.smem_bytes;
   }
   dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.m_tiles, (unsigned)pl.splits);
-  kern<<<grid, kQuantThreads, pl.smem_bytes, st>>>(tw, tx, p);
+  b2l_launch(kern, dim3(grid), dim3(kQuantThreads), (size_t)(pl.smem_bytes), st, tw, tx, p);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
 }
@@ -792,7 +814,7 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   pl = quant_plan(qk, m, n, k, seg_len);
   p.max_groups = groups_touched(pl.kb_per_split, seg_len);
   p.y = y; p.ldy = y_row_stride; p.M = (int)m; p.N = (int)n; p.K = (int)k;
-  p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.num_kb = pl.num_kb; p.w_stages = pl.stages; p.x_stages = pl.x_stages; p.pdl = 0;
+  p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.num_kb = pl.num_kb; p.w_stages = pl.stages; p.x_stages = pl.x_stages;
   p.timeline = g_timeline;
   p.debug = g_debug;
   p.x = x; p.ldx = x_row_stride;

@@ -92,6 +92,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, blk = blockIdx.y;
+  pdl_prologue();                                   // num_post / expert_ids / sorted ids are the align kernel's output
   const int num_post = *p.num_post;
   if (blk * BT >= num_post) return;                 // whole CTA: nothing routed to this block
   const int expert = p.expert_ids[blk];
@@ -340,7 +341,7 @@ static int launch_moe(const CUtensorMap& tw, const MoeParams& p, const MoePlan& 
     configured = pl.smem;
   }
   dim3 grid((unsigned)n_tiles, (unsigned)max_blocks);
-  kern<<<grid, kMoeThreads, pl.smem, st>>>(tw, p);
+  b2l_launch(kern, dim3(grid), dim3(kMoeThreads), (size_t)(pl.smem), st, tw, p);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
 }

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(kAlignThreads)
 moe_align_kernel(const void* __restrict__ topk_ids, int id_width, int num_slots, int block_size, int num_experts,
                  int32_t* __restrict__ sorted_ids, int32_t* __restrict__ expert_ids, int32_t* __restrict__ num_post,
                  int max_padded, int max_blocks) {
+  pdl_prologue();
   extern __shared__ int smem_i[];
   int* hist = smem_i;                                  // [kAlignWarps][E] per-warp chunk histograms
   int* starts = hist + kAlignWarps * num_experts;      // [E] padded start of each expert
@@ -82,6 +83,7 @@ moe_align_kernel(const void* __restrict__ topk_ids, int id_width, int num_slots,
 template <typename T, int MAXV>
 __global__ void moe_route_kernel(const T* __restrict__ logits, int64_t row_stride, int tokens, int num_experts,
                                  int top_k, int renorm, T* __restrict__ out_w, int64_t* __restrict__ out_ids) {
+  pdl_prologue();
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
   const int lane = threadIdx.x & 31;
@@ -156,7 +158,7 @@ extern "C" int b2l_moe_align_block_size(const void* topk_ids, int id_width, int6
     B2L_CUDA_CHECK(cudaFuncSetAttribute(moe_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  moe_align_kernel<<<1, kAlignThreads, smem, (cudaStream_t)stream>>>(
+  b2l_launch(moe_align_kernel, dim3(1), dim3(kAlignThreads), (size_t)(smem), (cudaStream_t)stream, 
       topk_ids, id_width, (int)num_slots, block_size, num_experts, (int32_t*)sorted_token_ids, (int32_t*)expert_ids,
       (int32_t*)num_tokens_post_padded, max_padded, max_blocks);
   B2L_LAUNCH_CHECK();
@@ -174,7 +176,7 @@ extern "C" int b2l_moe_route_topk(void* topk_weights, void* topk_ids_i64, const 
   const unsigned grid = (unsigned)cdiv64(tokens, warps);
   cudaStream_t st = (cudaStream_t)stream;
 #define ROUTE_LAUNCH(TT, MV)                                                                              \
-  moe_route_kernel<TT, MV><<<grid, warps * 32, 0, st>>>((const TT*)router_logits, row_stride, (int)tokens, \
+  b2l_launch(moe_route_kernel<TT, MV>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (const TT*)router_logits, row_stride, (int)tokens, \
                                                        num_experts, top_k, renormalize, (TT*)topk_weights, \
                                                        (int64_t*)topk_ids_i64)
 #define ROUTE_DISPATCH(TT)                                  \

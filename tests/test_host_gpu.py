@@ -149,3 +149,49 @@ def test_greedy_decode_loop_matches_step_by_step_api():
         got.append(loop.next_tokens.cpu().clone())
     assert torch.equal(torch.stack(got), torch.stack(expect))
     assert loop.launches_per_step > 0
+
+
+def test_programmatic_dependent_launch_is_bit_identical():
+    """Every kernel is launched with the programmatic-stream-serialisation attribute (csrc/common.cuh): the next
+    kernel's set-up and weight prefetch overlap the running one. Overlap must never change a result: the same
+    decode steps with the attribute off, on (eager) and on (captured graph) give identical logits."""
+    from lite_llama_b200 import _lib
+
+    cfg, runner, _ = _build("tiny-llama", "int4", max_seq_len=256, batch=4)
+    lib = _lib.load()
+    B, P = 4, 20
+    lens = torch.tensor([20, 3, 11, 16]).cuda()
+    ids = torch.randint(0, cfg.vocab_size, (B, P)).cuda()
+    pos = torch.arange(P).repeat(B, 1).cuda()
+    b_req = torch.arange(B).cuda()
+
+    def run(pdl: int, graph: bool):
+        old = lib.b2l_set_pdl(pdl)
+        try:
+            runner.kv_cache_manager.free_all()
+            runner.prefill_alloc_kv_cache(P, lens.clone(), b_req)
+            logits = runner.forward(ids, pos, last_token_index=lens - 1)
+            outs = [logits[:, -1].clone()]
+            tok = logits[:, -1].argmax(-1)
+            p = lens.clone().view(B, 1)
+            for _ in range(8):
+                runner.decode_alloc_kv_cache(B)
+                out = runner.forward(tok.view(B, 1), p) if graph else runner.model.forward(tok.view(B, 1), p, runner.atten_info)
+                outs.append(out[:, -1].clone())
+                tok = out[:, -1].argmax(-1)
+                p = p + 1
+            torch.cuda.synchronize()
+            return torch.stack(outs).cpu()
+        finally:
+            lib.b2l_set_pdl(old)
+
+    serial = run(0, False)
+    overlapped = run(1, False)
+    assert torch.equal(serial, overlapped), "PDL changed a logit: a kernel touched upstream data before griddepcontrol.wait"
+    old = lib.b2l_set_pdl(1)
+    try:
+        runner.enable_cuda_graph(batch_sizes=(4,), seq_len_buckets=(256,))   # graph nodes keep the attribute they were captured with
+    finally:
+        lib.b2l_set_pdl(old)
+    graphed = run(1, True)
+    assert torch.equal(serial, graphed)

@@ -622,3 +622,48 @@ def test_fused_moe_zero_routing_weight_drops_the_slot():
     tw[:, 1] = 0
     out = K().fused_moe(x.cuda(), w1.cuda(), w2.cuda(), tw.cuda(), ids.cuda())
     close(out, ops.fused_moe(x, w1, w2, tw, ids), rtol=5e-3, atol=2e-3)
+
+
+# --------------------------------------------------------------------------- #
+# programmatic dependent launch: overlapped kernel chains must be bit-identical to serialised ones
+# --------------------------------------------------------------------------- #
+def test_pdl_kernel_chain_llama_shapes_bit_identical():
+    """One Llama-3-8B MLP block at batch 32 (rmsnorm -> gate|up W4A16 -> swiglu -> down W4A16), 12 rounds feeding
+    each round's output back in, with the launch attribute off and on. The GEMMs prefetch weights and scale tables
+    before griddepcontrol.wait; activations, outputs and the split-K workspace must only be touched after it."""
+    from lite_llama_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(0)
+    h, inter, m = 4096, 14336, 32
+    dev = "cuda"
+    qgu = torch.randint(-(2**31), 2**31 - 1, (2 * inter, h // 8), device=dev, dtype=torch.int64).to(torch.int32)
+    sgu = torch.rand(2 * inter, h // 128, device=dev) * 0.004
+    zgu = torch.randint(0, 16, (2 * inter, h // 128), device=dev).float()
+    qd = torch.randint(-(2**31), 2**31 - 1, (h, inter // 8), device=dev, dtype=torch.int64).to(torch.int32)
+    sd = torch.rand(h, inter // 128, device=dev) * 0.004
+    zd = torch.randint(0, 16, (h, inter // 128), device=dev).float()
+    wn = torch.ones(h, device=dev, dtype=torch.float16)
+    x0 = torch.randn(m, 1, h, device=dev, dtype=torch.float16)
+
+    def run(pdl):
+        old = lib.b2l_set_pdl(pdl)
+        try:
+            x = x0.clone()
+            res = torch.zeros_like(x0)
+            for _ in range(12):
+                y, res = K().skip_rmsnorm(x, res, wn, 1e-5)
+                gu = K().w4a16_matmul(y.view(m, h), qgu, sgu, zgu, group_size=128)
+                act = K().swiglu_forward(gu[:, :inter], gu[:, inter:])
+                x = K().w4a16_matmul(act, qd, sd, zd, group_size=128).view(m, 1, h)
+            torch.cuda.synchronize()
+            return x.cpu(), res.cpu()
+        finally:
+            lib.b2l_set_pdl(old)
+
+    a = run(0)
+    b = run(1)
+    c = run(1)
+    assert torch.isfinite(a[0].float()).all()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(b[0], c[0])
