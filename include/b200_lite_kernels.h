@@ -123,6 +123,10 @@ int b2l_linear(void* y, const void* x, const void* w, const void* bias, int64_t 
  * -- lite_llama/kernels/quantization/w4a16.py:152-207.  fp16 activations only (w4a16.py:174). */
 int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n, int64_t k, int64_t group_k);
 int64_t b2l_quant_gemm_num_counters(int64_t m, int64_t n);
+/* launch plan of a quantised GEMM, for tests and tools (no GPU work): out[10] = {stream-K CTAs (0 = tile x split
+ * grid), workspace slots per tile, raw blocks per tile, weight-row tiles, splits, k-blocks per split, weight ring
+ * depth, activation ring depth, shared-memory bytes, scale-table columns}.  The trailing argument is unused. */
+int b2l_quant_gemm_plan(int kind, int64_t m, int64_t n, int64_t k, int64_t group_k, int* out, void* reserved);
 int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, const void* scales, const void* zeros,
                      const void* bias, int bias_is_f32, int64_t m, int64_t n, int64_t k, int group_size,
                      int64_t x_row_stride, int64_t qw_row_stride, int64_t s_row_stride, int64_t s_col_stride,

@@ -30,6 +30,7 @@
 // 5-20 % of HBM peak before the current structure.
 #include "gemm_tc.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace gemm {
 
@@ -57,13 +58,33 @@ struct QuantParams {
   uint32_t* ws; int* counters;
   int M, N, K;
   int splits, kb_per_split, num_kb;
+  // Stream-K schedule (sk_ctas > 0; grid.x = sk_ctas, grid.z = 1): the (tile, raw block) space is linearised
+  // tile-major and CTA c owns the contiguous range [c*total/sk_ctas, (c+1)*total/sk_ctas) -- every SM streams the
+  // same number of weight bytes (+-1 raw block) whatever the tile count, instead of whole tiles in uneven waves.
+  // A range covers the tail of one tile, whole tiles, and the head of another ("pieces"); a tile shared by several
+  // CTAs is completed through the split-K workspace + ticket, slots in CTA order (deterministic).
+  int sk_ctas, sk_slots;                   // sk_slots: workspace slots per tile (max CTAs sharing one tile)
+  int n_tiles, nrb_tile;                   // weight-row tiles, raw blocks per tile (K / raw-block K)
   int w_stages, x_stages;                  // ring depths: raw weight blocks / activation blocks
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
   int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
   long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
   int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
-enum { DBG_FORCE_XSUM = 8 };
+// DBG_RAW_OPERAND: skip the int4 -> fp16 arithmetic (operand = raw bits): how much of the time is the ALU pipe?
+// DBG_PAIR_K4: extract nibble pairs (k, k+4) with one LOP3 + HFMA2 each (5 ALU-pipe instructions per word instead
+// of 8) WITHOUT permuting the activations -- prices a pre-shuffled activation layout.  DBG_NO_STREAMK: host side.
+// DBG_SKIP_DRAIN: only the last segment of a piece is read back from TMEM (prices a scale-folded operand).
+enum { DBG_FORCE_XSUM = 8, DBG_RAW_OPERAND = 16, DBG_PAIR_K4 = 32, DBG_NO_STREAMK = 64, DBG_SKIP_DRAIN = 128,
+       DBG_FEW_MMA = 256 /* issue 1 of every 4 MMAs */, DBG_NO_STTM = 512 /* skip the TMEM operand store */,
+       DBG_WAIT_SPIN = 1024 /* mbarrier.test_wait polling */, DBG_WAIT_SHORT = 2048 /* try_wait without the long suspend hint */,
+       DBG_NO_XLOAD = 4096 /* activation tiles are never fetched */, DBG_HALF_RING = 8192 /* half the weight ring depth */ };
+__device__ __forceinline__ void qwait(uint64_t* bar, uint32_t parity, int debug) {
+  if (debug & DBG_WAIT_SPIN) mbar_wait_spin(bar, parity);
+  else if (debug & DBG_WAIT_SHORT) mbar_wait_short(bar, parity);
+  else mbar_wait(bar, parity);
+}
+constexpr int kTlCta = 4096;    // timeline: [1024][3] per-CTA {globaltimer at entry, at exit, SM id}
 constexpr int kTlMisc = 3072;   // timeline: start-up / shutdown stamps of CTA (0,0,0), see tools/timeline.py
 
 // role rows of the debug timeline
@@ -72,6 +93,9 @@ enum { TL_PROD = 0, TL_MMA_READY = 1, TL_MMA_ISSUED = 2, TL_DQ_START = 3, TL_DQ_
   do {                                                                                        \
     if (tl && (idx) < 256 && lane == 0) tl[(role) * 256 + (idx)] = clock64();                 \
   } while (0)
+
+static long long* g_timeline = nullptr;   // set through b2l_debug_set_timeline (tools/timeline.py)
+static int g_debug = 0;                   // b2l_debug_set_flags
 
 struct __align__(8) QControl {
   uint64_t w_full[kMaxRawStages];
@@ -87,6 +111,38 @@ struct __align__(8) QControl {
   int is_last;
 };
 static_assert(sizeof(QControl) <= 1024, "control block too large");
+
+// One CTA's share of the work: pieces (tile, raw-block range) in processing order.  Legacy grid: exactly one piece
+// (tile = blockIdx.x, k-range of split blockIdx.z).  Everything that indexes rings, TMEM stages, accumulator buffers
+// and the scale table counts raw blocks / segments LINEARLY over the CTA's pieces, so only the code that touches
+// global memory (TMA coordinates, table staging, output) looks at the tile.
+struct Piece {
+  int n_tile;
+  int rb_lo, rb_hi;      // raw blocks [rb_lo, rb_hi) of the tile's K range
+};
+struct WorkRange {
+  int npieces;
+  int total_rb;          // raw blocks of this CTA over all pieces
+  int t0, g0, g1;        // stream-K: first tile, linear raw-block range
+  int nrb_tile;
+  int legacy_tile, legacy_lo, legacy_hi;
+  __device__ __forceinline__ Piece piece(int i) const {
+    Piece pc;
+    if (nrb_tile == 0) {
+      pc.n_tile = legacy_tile; pc.rb_lo = legacy_lo; pc.rb_hi = legacy_hi;
+    } else {
+      pc.n_tile = t0 + i;
+      const int base = pc.n_tile * nrb_tile;
+      pc.rb_lo = g0 > base ? g0 - base : 0;
+      pc.rb_hi = g1 - base < nrb_tile ? g1 - base : nrb_tile;
+    }
+    return pc;
+  }
+};
+// first / last stream-K CTA that owns a raw block of tile t
+__device__ __forceinline__ int sk_owner(int lin_rb, int ctas, int total) {
+  return (int)((((long long)lin_rb + 1) * ctas - 1) / total);
+}
 
 // Four TMEM accumulator buffers: the epilogue's drain latency (wake-up, tcgen05.ld, FMAs, arrive) is several
 // hundred cycles per segment; with only two buffers the MMA warps stalled on acc_empty (ncu: profiles/).
@@ -205,7 +261,7 @@ __device__ __forceinline__ void st_release_smem(int* p, int v) {
 // instructions per step in the generic loop cost 160 cycles per MMA against 16 cycles of tensor-pipe time.
 template <int QK, int BT, int SEG_STEPS>
 __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_base, uint32_t a_base, uint64_t bdesc0,
-                                                int seg0, int gsub0, uint64_t* x_empty, long long* tl) {
+                                                int seg0, int gsub0, uint64_t* x_empty, long long* tl, int debug = 0) {
   constexpr int RW = raw_sub<QK>();
   constexpr int NSEG = RW * 4 / SEG_STEPS;
   constexpr int SPS = SEG_STEPS / 4;              // operand sub-blocks per segment
@@ -217,11 +273,11 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
     const int seg = seg0 + s;
     const int buf = seg & (NB - 1);
     // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
-    mbar_wait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1);
+    qwait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1, debug);
 #pragma unroll
     for (int q = 0; q < SPS; ++q) {
       const int gsub = gsub0 + s * SPS + q;
-      mbar_wait(&ctl->op_full[gsub % kOpStages], (gsub / kOpStages) & 1);
+      qwait(&ctl->op_full[gsub % kOpStages], (gsub / kOpStages) & 1, debug);
     }
     tc_fence_after();
     if (tl && seg < 128 && (threadIdx.x & 31) == 0) tl[2048 + seg * 2] = clock64();
@@ -231,8 +287,9 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
       for (int j = 0; j < SEG_STEPS; ++j) {
         const int st = s * SEG_STEPS + j;
         const int ostage = (gsub0 + (st >> 2)) % kOpStages;
-        umma_f16_ts(d, a_base + ostage * 32 + (st & 3) * 8,
-                    bdesc0 + (uint64_t)((((st >> 2) * kXBytes) >> 4) + 2 * (st & 3)), idesc, j > 0 ? 1u : 0u);
+        if (!(debug & DBG_FEW_MMA) || (st & 3) == 3)
+          umma_f16_ts(d, a_base + ostage * 32 + (st & 3) * 8,
+                      bdesc0 + (uint64_t)((((st >> 2) * kXBytes) >> 4) + 2 * (st & 3)), idesc, j > 0 ? 1u : 0u);
         if ((st & 3) == 3) tc_commit(&ctl->op_empty[ostage]);
       }
       tc_commit(&ctl->acc_full[buf]);
@@ -276,22 +333,52 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   static_assert(kColsUsed <= 512, "TMEM budget exceeded");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int m_tile = blockIdx.y;
   long long* tl = (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.timeline : nullptr;
-  const int kb0 = split * p.kb_per_split;
-  const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
-  const int nkb = kb1 - kb0;
-  const int nrb = (nkb + RW - 1) / RW;            // raw blocks of this CTA
   const int seg_len = p.group_k;                  // K elements per scale group (multiple of 16)
-  const int k_begin = kb0 * 64;
-  int k_end = kb1 * 64; if (k_end > p.K) k_end = p.K;
-  // segments: maximal runs of 16-element MMA steps inside one scale group and inside [k_begin, k_end)
-  const int steps_total = (k_end - k_begin + 15) / 16;
+  // ---- this CTA's work: pieces (tile, raw-block range); see struct Piece ----
+  WorkRange wr;
+  int k_begin, steps_total;                       // legacy grid only: the single piece's first K and its MMA steps
+  if (p.sk_ctas > 0) {
+    const int total = p.n_tiles * p.nrb_tile;
+    wr.nrb_tile = p.nrb_tile;
+    wr.g0 = (int)(((long long)blockIdx.x * total) / p.sk_ctas);
+    wr.g1 = (int)(((long long)(blockIdx.x + 1) * total) / p.sk_ctas);
+    wr.t0 = wr.g0 / p.nrb_tile;
+    wr.npieces = (wr.g1 - 1) / p.nrb_tile - wr.t0 + 1;
+    wr.total_rb = wr.g1 - wr.g0;
+    wr.legacy_tile = wr.legacy_lo = wr.legacy_hi = 0;
+    k_begin = 0;
+    steps_total = wr.total_rb * RW * 4;            // stream-K needs K to be a whole number of raw blocks
+  } else {
+    const int kb0 = blockIdx.z * p.kb_per_split;  // kb_per_split is a multiple of RW
+    const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
+    wr.nrb_tile = 0; wr.g0 = wr.g1 = wr.t0 = 0;
+    wr.npieces = 1;
+    wr.legacy_tile = blockIdx.x;
+    wr.legacy_lo = kb0 / RW;
+    wr.legacy_hi = (kb1 + RW - 1) / RW;
+    wr.total_rb = wr.legacy_hi - wr.legacy_lo;
+    k_begin = kb0 * 64;
+    int k_end = kb1 * 64; if (k_end > p.K) k_end = p.K;
+    // segments: maximal runs of 16-element MMA steps inside one scale group and inside [k_begin, k_end)
+    steps_total = (k_end - k_begin + 15) / 16;
+  }
+  const int nrb = wr.total_rb;                    // raw blocks of this CTA
   // two MMA warps (alternate raw blocks) when no segment spans two raw blocks, else warp 1 alone
   const int mma_warps = p.aligned ? 2 : 1;
 
   pdl_launch_dependents();   // the next kernel may set itself up while this one streams weights (common.cuh)
   if (tl && threadIdx.x == 0) tl[kTlMisc + 0] = clock64();
+  // every CTA: wall-clock (globaltimer, ns) at entry and exit + its SM id -> who is the straggler, and what is the
+  // real SM clock (CTA 0 also stamps clock64 at both ends)
+  if (p.timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.timeline[kTlCta + 3 * blockIdx.x] = (long long)gt;
+    p.timeline[kTlCta + 3 * blockIdx.x + 2] = (long long)smid;
+  }
 
   if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
     // Stage this CTA's scale / zero-point rows FIRST: the dequant warps cannot convert a single weight before the
@@ -301,31 +388,56 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // 16 bytes (4 groups) per cp.async when the row is contiguous and aligned.  The tables are weights (static),
     // so this runs before griddepcontrol.wait.
     const int epi_tid = (warp & 3) * 32 + lane;
-    const int n = n_tile * kBlockW + epi_tid;
-    const int g_first = k_begin / seg_len;
-    const int g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
-    if (n < p.N) {
-      const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g_first * p.s_stride_k;
-      const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n + (int64_t)g_first * p.s_stride_k : nullptr;
-      float* sdst = scale_tab + epi_tid * tab_pitch;
-      float* zdst = zero_tab + epi_tid * tab_pitch;
-      const bool vec = p.s_stride_k == 1 && ((uintptr_t)srow % 16 == 0) && (QK != Q_INT4 || (uintptr_t)zrow % 16 == 0);
-      int g = 0;
-      if (vec) {
+    float* sdst = scale_tab + epi_tid * tab_pitch;
+    float* zdst = zero_tab + epi_tid * tab_pitch;
+    int tcol = 0;                                            // table column = scale group, linear over the pieces
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      const int n = pc.n_tile * kBlockW + epi_tid;
+      int g_first, g_count;
+      if (p.sk_ctas > 0) {
+        g_first = pc.rb_lo * kRawK / seg_len;
+        g_count = (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
+      } else {
+        g_first = k_begin / seg_len;
+        g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+      }
+      if (n < p.N) {
+        const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g_first * p.s_stride_k;
+        const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n + (int64_t)g_first * p.s_stride_k : nullptr;
+        // widest copy both sides allow (source and destination columns may differ in alignment under stream-K)
+        int w = 1;
+        if (p.s_stride_k == 1) {
+          const uintptr_t a = (uintptr_t)srow | (uintptr_t)(sdst + tcol) | (QK == Q_INT4 ? ((uintptr_t)zrow | (uintptr_t)(zdst + tcol)) : 0);
+          w = (a % 16 == 0) ? 4 : (a % 8 == 0) ? 2 : 1;
+        }
+        int g = 0;
         // zero points first: they gate the dequant warps, the scales are only needed by the first drain
-        if (QK == Q_INT4)
-          for (int gz = 0; gz + 4 <= g_count; gz += 4)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(zdst + gz)), "l"(zrow + gz) : "memory");
-        for (; g + 4 <= g_count; g += 4)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + g)), "l"(srow + g) : "memory");
+        if (w == 4) {
+          if (QK == Q_INT4)
+            for (int gz = 0; gz + 4 <= g_count; gz += 4)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(zdst + tcol + gz)), "l"(zrow + gz) : "memory");
+          for (; g + 4 <= g_count; g += 4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + tcol + g)), "l"(srow + g) : "memory");
+        } else if (w == 2) {
+          if (QK == Q_INT4)
+            for (int gz = 0; gz + 2 <= g_count; gz += 2)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(zdst + tcol + gz)), "l"(zrow + gz) : "memory");
+          for (; g + 2 <= g_count; g += 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst + tcol + g)), "l"(srow + g) : "memory");
+        }
+        for (; g < g_count; ++g) {
+          if (QK == Q_INT4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zdst + tcol + g)),
+                         "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst + tcol + g)),
+                       "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
+        }
+      } else {
+        // rows past N: benign values so that the zero-point check below never trips on garbage
+        for (int g = 0; g < g_count; ++g) { sdst[tcol + g] = 0.f; if (QK == Q_INT4) zdst[tcol + g] = 0.f; }
       }
-      for (; g < g_count; ++g) {
-        if (QK == Q_INT4)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zdst + g)),
-                       "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst + g)),
-                     "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
-      }
+      tcol += g_count;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -367,34 +479,43 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // Weights are static: under programmatic dependent launch this stream starts while the previous kernel
     // is still running (no griddepcontrol.wait on this path).
     PipeState ws(p.w_stages);
-    for (int rb = 0; rb < nrb; ++rb) {
-      mbar_wait(&ctl->w_empty[ws.stage], ws.phase ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&ctl->w_full[ws.stage], kABytes);       // OOB parts are zero-filled but still counted
-        const int kb = kb0 + rb * RW;                                  // first 64-element k-block of this raw block
-        tma_load_2d_hint(w_ring + (size_t)ws.stage * kABytes, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64,
-                         n_tile * kBlockW, &ctl->w_full[ws.stage], kEvictFirst);
+    int lin = 0;
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      for (int rb = pc.rb_lo; rb < pc.rb_hi; ++rb, ++lin) {
+        qwait(&ctl->w_empty[ws.stage], ws.phase ^ 1, p.debug);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&ctl->w_full[ws.stage], kABytes);     // OOB parts are zero-filled but still counted
+          const int kb = rb * RW;                                      // first 64-element k-block of this raw block
+          tma_load_2d_hint(w_ring + (size_t)ws.stage * kABytes, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64,
+                           pc.n_tile * kBlockW, &ctl->w_full[ws.stage], kEvictFirst);
+        }
+        __syncwarp();
+        TL_STAMP(TL_PROD, lin);
+        ws.advance();
       }
-      __syncwarp();
-      TL_STAMP(TL_PROD, rb);
-      ws.advance();
     }
   } else if (warp == kWarpXProd) {
     // ===================== activation producer =====================
     pdl_wait_prior();                        // the activations are the previous kernel's output
     PipeState xs(p.x_stages);
-    for (int rb = 0; rb < nrb; ++rb) {
-      mbar_wait(&ctl->x_empty[xs.stage], xs.phase ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&ctl->x_full[xs.stage], kXStage);
-        const int kb = kb0 + rb * RW;
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      for (int rb = pc.rb_lo; rb < pc.rb_hi; ++rb) {
+        qwait(&ctl->x_empty[xs.stage], xs.phase ^ 1, p.debug);
+        if (p.debug & DBG_NO_XLOAD) {
+          if (elect_one()) mbar_arrive(&ctl->x_full[xs.stage]);
+        } else if (elect_one()) {
+          mbar_arrive_expect_tx(&ctl->x_full[xs.stage], kXStage);
+          const int kb = rb * RW;
 #pragma unroll
-        for (int sub = 0; sub < RW; ++sub)
-          tma_load_2d_hint(x_ring + (size_t)xs.stage * kXStage + sub * kXBytes, &tmap_x, (kb + sub) * 64, m_tile * BT,
-                           &ctl->x_full[xs.stage], kEvictLast);
+          for (int sub = 0; sub < RW; ++sub)
+            tma_load_2d_hint(x_ring + (size_t)xs.stage * kXStage + sub * kXBytes, &tmap_x, (kb + sub) * 64, m_tile * BT,
+                             &ctl->x_full[xs.stage], kEvictLast);
+        }
+        __syncwarp();
+        xs.advance();
       }
-      __syncwarp();
-      xs.advance();
     }
   } else if (warp == kWarpMma0 || warp == kWarpMma1) {
     // ===================== MMA issuers =====================
@@ -409,11 +530,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       int seg_left = ((k_begin / seg_len + 1) * seg_len - k_begin) / 16;   // steps until the open segment closes
       if (seg_left > steps_total) seg_left = steps_total;
       bool seg_open = false;
+      int rstage = mma_idx % p.x_stages;
+      uint32_t rphase = (mma_idx / p.x_stages) & 1;
       for (int rb = mma_idx; rb < nrb; rb += mma_warps) {
-        const int rstage = rb % p.x_stages;
         const int gsub0 = rb * RW;                                       // first operand sub-block of this raw block
         TL_STAMP(7, rb);
-        mbar_wait(&ctl->x_full[rstage], (rb / p.x_stages) & 1);          // activation sub-tiles (TMA)
+        qwait(&ctl->x_full[rstage], rphase, p.debug);                         // activation sub-tiles (TMA)
         tc_fence_after();
         TL_STAMP(TL_MMA_READY, rb);
         int steps_here = steps_total - rb * (RW * 4);
@@ -428,9 +550,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (mma_warps == 2 && steps_here == RW * 4) {
           // aligned mode: 1 or 2 whole segments per raw block
           if (seg_steps == RW * 4)
-            issue_raw_block<QK, BT, RW * 4>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl);
+            issue_raw_block<QK, BT, RW * 4>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, p.debug);
           else
-            issue_raw_block<QK, BT, RW * 2>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl);
+            issue_raw_block<QK, BT, RW * 2>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, p.debug);
         } else if (elect_one()) {
 #pragma unroll
           for (int st = 0; st < RW * 4; ++st) {
@@ -438,12 +560,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               const int buf = seg % NB;
               const int ostage = (gsub0 + (st >> 2)) % kOpStages;
               if ((st & 3) == 0) {
-                mbar_wait(&ctl->op_full[ostage], ((gsub0 + (st >> 2)) / kOpStages) & 1);   // dequantised sub-block
+                qwait(&ctl->op_full[ostage], ((gsub0 + (st >> 2)) / kOpStages) & 1, p.debug);   // dequantised sub-block
                 tc_fence_after();
               }
               if (!seg_open) {
                 // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
-                mbar_wait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1);
+                qwait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1, p.debug);
                 tc_fence_after();
               }
               const uint64_t bdesc = bdesc0 + (uint64_t)(((st >> 2) * kXBytes) >> 4) + 2 * (st & 3);
@@ -466,23 +588,26 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
         __syncwarp();
         TL_STAMP(TL_MMA_ISSUED, rb);
+        rstage += mma_warps;
+        if (rstage >= p.x_stages) { rstage -= p.x_stages; rphase ^= 1; }
       }
     }
   } else if (warp >= kWarpEpi0) {
     // ===================== epilogue (warps 8..11) =====================
     const int quad = warp & 3;
     const int epi_tid = quad * 32 + lane;
-    const int n = n_tile * kBlockW + epi_tid;
-    const bool n_ok = n < p.N;
-    const int tile_id = m_tile * gridDim.x + n_tile;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float acc[BT];
 #pragma unroll
     for (int j = 0; j < BT; ++j) acc[j] = 0.f;
 
     // this row's scales / zero points were requested at kernel entry (see above); wait for them here
-    const int g_first = k_begin / seg_len;
-    const int g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+    int tab_cols = 0;                                      // table columns in use (scale groups over all pieces)
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      if (p.sk_ctas > 0) tab_cols += (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
+      else tab_cols += (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len + 1;
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // every thread reads back only its own row
     if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 2] = clock64();
 
@@ -493,11 +618,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     bool need_xsum = false;
     if (QK == Q_INT4) {
       bool bad = p.force_xsum || (p.debug & DBG_FORCE_XSUM);
-      if (n_ok)
-        for (int g = 0; g < g_count; ++g) {
-          const float z = zero_tab[epi_tid * tab_pitch + g];
-          bad |= !(z >= 0.f && z <= 1023.f && z == rintf(z));
-        }
+      for (int g = 0; g < tab_cols; ++g) {                 // rows past N hold zeros
+        const float z = zero_tab[epi_tid * tab_pitch + g];
+        bad |= !(z >= 0.f && z <= 1023.f && z == rintf(z));
+      }
       if (bad) atomicOr(&ctl->need_xsum, 1);
       asm volatile("bar.sync 4, 384;" ::: "memory");        // with the 8 dequant warps: tables + flag are visible
       need_xsum = ctl->need_xsum != 0;
@@ -506,119 +630,147 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 3] = clock64();
     constexpr int PARTS = 128 / BT;
     const int xs_m = epi_tid / PARTS, xs_part = epi_tid % PARTS;
+    T* y = reinterpret_cast<T*>(p.y);
 
-    // enumerate segments exactly like the MMA warps do
-    int k_pos = k_begin;
-    int seg = 0;
-    const int k_lim = k_begin + steps_total * 16;
-    int g = g_first;                                   // scale group of the open segment (no division in the loop)
-    int k_group_end = (g_first + 1) * seg_len;
-    while (k_pos < k_lim) {
-      const int k_next = k_group_end < k_lim ? k_group_end : k_lim;
-      if (QK == Q_INT4 && need_xsum) {
-        // thread -> token m = tid / PARTS, an interleaved share of the segment's 8-element chunks
-        float xsum_m = 0.f;
-        const int m = m_tile * BT + xs_m;
-        if (m < p.M) {
-          const __half* xrow = reinterpret_cast<const __half*>(p.x) + (int64_t)m * p.ldx;
-          for (int k = k_pos + xs_part * 8; k < k_next; k += PARTS * 8) {
-            if (k + 8 <= p.K) {
-              const uint4 v = ldg_128(xrow + k);
-              const __half2* h = reinterpret_cast<const __half2*>(&v);
+    int seg = 0;                                           // segments and table columns run linearly over the pieces
+    int tcol = 0;
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      const int n = pc.n_tile * kBlockW + epi_tid;
+      const bool n_ok = n < p.N;
+      // enumerate this piece's segments exactly like the MMA warps do
+      int k_pos, k_lim;
+      if (p.sk_ctas > 0) { k_pos = pc.rb_lo * kRawK; k_lim = pc.rb_hi * kRawK; }
+      else { k_pos = k_begin; k_lim = k_begin + steps_total * 16; }
+      int k_group_end = (k_pos / seg_len + 1) * seg_len;   // end of the open segment's scale group
+      while (k_pos < k_lim) {
+        const int k_next = k_group_end < k_lim ? k_group_end : k_lim;
+        if (QK == Q_INT4 && need_xsum) {
+          // thread -> token m = tid / PARTS, an interleaved share of the segment's 8-element chunks
+          float xsum_m = 0.f;
+          const int m = m_tile * BT + xs_m;
+          if (m < p.M) {
+            const __half* xrow = reinterpret_cast<const __half*>(p.x) + (int64_t)m * p.ldx;
+            for (int k = k_pos + xs_part * 8; k < k_next; k += PARTS * 8) {
+              if (k + 8 <= p.K) {
+                const uint4 v = ldg_128(xrow + k);
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __half22float2(h[q]);
-                xsum_m += f.x + f.y;
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __half22float2(h[q]);
+                  xsum_m += f.x + f.y;
+                }
+              } else {
+                for (int kk = k; kk < p.K; ++kk) xsum_m += __half2float(xrow[kk]);
               }
-            } else {
-              for (int kk = k; kk < p.K; ++kk) xsum_m += __half2float(xrow[kk]);
             }
           }
+#pragma unroll
+          for (int o = 1; o < PARTS && o < 32; o <<= 1) xsum_m += __shfl_xor_sync(0xffffffffu, xsum_m, o);
+          // exchange: every thread needs all BT sums
+          float* xs = xs_smem + (seg & 1) * BT;
+          if (xs_part == 0) xs[xs_m] = xsum_m;
+          asm volatile("bar.sync 3, 128;" ::: "memory");
         }
-#pragma unroll
-        for (int o = 1; o < PARTS && o < 32; o <<= 1) xsum_m += __shfl_xor_sync(0xffffffffu, xsum_m, o);
-        // exchange: every thread needs all BT sums
-        float* xs = xs_smem + (seg & 1) * BT;
-        if (xs_part == 0) xs[xs_m] = xsum_m;
-        asm volatile("bar.sync 3, 128;" ::: "memory");
-      }
-      const int buf = seg % NB;
-      float sc = 0.f, zp = 0.f;
-      if (n_ok) {
-        sc = lds_f32(scale_tab + epi_tid * tab_pitch + (g - g_first));
-        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + epi_tid * tab_pitch + (g - g_first));
-      }
-      mbar_wait(&ctl->acc_full[buf], (seg / NB) & 1);
-      tc_fence_after();
-      if (warp == kWarpEpi0) TL_STAMP(TL_EPI_START, seg);
-      const uint32_t ta = taddr + buf * BT;
-      constexpr int CH = BT < 32 ? BT : 32;                  // columns drained per tcgen05.wait::ld
-      const float4* xs4 = reinterpret_cast<const float4*>(xs_smem + (seg & 1) * BT);
-#pragma unroll
-      for (int c0 = 0; c0 < BT; c0 += CH) {
-        uint32_t pv[CH];
-#pragma unroll
-        for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
-        tc_wait_ld();
-        if (c0 + CH == BT) {
-          // the accumulator is in registers: hand the buffer back before doing the arithmetic
+        const int buf = seg % NB;
+        const float sc = lds_f32(scale_tab + epi_tid * tab_pitch + tcol);        // rows past N hold zeros
+        float zp = 0.f;
+        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + epi_tid * tab_pitch + tcol);
+        qwait(&ctl->acc_full[buf], (seg / NB) & 1, p.debug);
+        tc_fence_after();
+        if (warp == kWarpEpi0) TL_STAMP(TL_EPI_START, seg);
+        if ((p.debug & DBG_SKIP_DRAIN) && k_next < k_lim) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+          k_pos = k_next; k_group_end += seg_len; ++tcol; ++seg;
+          continue;
         }
-        if (QK == Q_INT4 && need_xsum) {
+        const uint32_t ta = taddr + buf * BT;
+        constexpr int CH = BT < 32 ? BT : 32;                  // columns drained per tcgen05.wait::ld
+        const float4* xs4 = reinterpret_cast<const float4*>(xs_smem + (seg & 1) * BT);
 #pragma unroll
-          for (int j4 = 0; j4 < CH / 4; ++j4) {
-            const float4 x4 = xs4[c0 / 4 + j4];
-            float* a4 = acc + c0 + 4 * j4;
-            a4[0] = fmaf(sc, fmaf(-zp, x4.x, __uint_as_float(pv[4 * j4 + 0])), a4[0]);
-            a4[1] = fmaf(sc, fmaf(-zp, x4.y, __uint_as_float(pv[4 * j4 + 1])), a4[1]);
-            a4[2] = fmaf(sc, fmaf(-zp, x4.z, __uint_as_float(pv[4 * j4 + 2])), a4[2]);
-            a4[3] = fmaf(sc, fmaf(-zp, x4.w, __uint_as_float(pv[4 * j4 + 3])), a4[3]);
+        for (int c0 = 0; c0 < BT; c0 += CH) {
+          uint32_t pv[CH];
+#pragma unroll
+          for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
+          tc_wait_ld();
+          if (c0 + CH == BT) {
+            // the accumulator is in registers: hand the buffer back before doing the arithmetic
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
           }
-        } else {
+          if (QK == Q_INT4 && need_xsum) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) acc[c0 + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c0 + j]);
+            for (int j4 = 0; j4 < CH / 4; ++j4) {
+              const float4 x4 = xs4[c0 / 4 + j4];
+              float* a4 = acc + c0 + 4 * j4;
+              a4[0] = fmaf(sc, fmaf(-zp, x4.x, __uint_as_float(pv[4 * j4 + 0])), a4[0]);
+              a4[1] = fmaf(sc, fmaf(-zp, x4.y, __uint_as_float(pv[4 * j4 + 1])), a4[1]);
+              a4[2] = fmaf(sc, fmaf(-zp, x4.z, __uint_as_float(pv[4 * j4 + 2])), a4[2]);
+              a4[3] = fmaf(sc, fmaf(-zp, x4.w, __uint_as_float(pv[4 * j4 + 3])), a4[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[c0 + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c0 + j]);
+          }
         }
+        if (warp == kWarpEpi0) TL_STAMP(TL_EPI_DONE, seg);
+        k_pos = k_next;
+        k_group_end += seg_len;
+        ++tcol;
+        ++seg;
       }
-      if (warp == kWarpEpi0) TL_STAMP(TL_EPI_DONE, seg);
-      k_pos = k_next;
-      k_group_end += seg_len;
-      ++g;
-      ++seg;
-    }
 
-    if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 5] = clock64();
-    pdl_wait_prior();                // output / workspace buffers may still be in use by the previous kernel
-    T* y = reinterpret_cast<T*>(p.y);
-    auto store_final = [&]() {
-      if (!n_ok) return;
-      float bv = 0.f;
-      if (p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
-                                     : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+      // ---- the piece is complete: write the tile, or hand the partial sum to the tile's last finisher ----
+      if (tl && warp == kWarpEpi0 && lane == 0 && pi == wr.npieces - 1) tl[kTlMisc + 5] = clock64();
+      pdl_wait_prior();              // output / workspace buffers may still be in use by the previous kernel
+      auto store_final = [&]() {
+        if (!n_ok) return;
+        float bv = 0.f;
+        if (p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
+                                       : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
 #pragma unroll
-      for (int j = 0; j < BT; ++j) {
-        const int m = m_tile * BT + j;
-        if (m < p.M) y[(int64_t)m * p.ldy + n] = __float2half_rn(acc[j] + bv);
-      }
-    };
-    if (p.splits == 1) {
-      store_final();
-    } else {
-      uint32_t* mine = p.ws + ((size_t)tile_id * p.splits + split) * (BT * kBlockW);
-#pragma unroll
-      for (int j = 0; j < BT; ++j) mine[j * kBlockW + epi_tid] = __float_as_uint(acc[j]);
-      if (splitk_ticket(p.counters, tile_id, p.splits, epi_tid, &ctl->is_last)) {
-        const uint32_t* base = p.ws + (size_t)tile_id * p.splits * (BT * kBlockW);
-#pragma unroll
-        for (int j = 0; j < BT; ++j) acc[j] = 0.f;
-        for (int s = 0; s < p.splits; ++s) {
-          const uint32_t* src = base + (size_t)s * (BT * kBlockW) + epi_tid;
-#pragma unroll
-          for (int j = 0; j < BT; ++j) acc[j] += __uint_as_float(__ldcg(src + j * kBlockW));
+        for (int j = 0; j < BT; ++j) {
+          const int m = m_tile * BT + j;
+          if (m < p.M) y[(int64_t)m * p.ldy + n] = __float2half_rn(acc[j] + bv);
         }
-        store_final();
+      };
+      // who shares this tile: legacy grid = the p.splits CTAs along grid.z; stream-K = the CTAs whose ranges
+      // overlap the tile's raw blocks, slot = position among them (CTA order => deterministic sum order)
+      int sharers, slot, slots_per_tile;
+      if (p.sk_ctas > 0) {
+        const int total = p.n_tiles * p.nrb_tile;
+        const int c_lo = sk_owner(pc.n_tile * p.nrb_tile, p.sk_ctas, total);
+        const int c_hi = sk_owner((pc.n_tile + 1) * p.nrb_tile - 1, p.sk_ctas, total);
+        sharers = c_hi - c_lo + 1;
+        slot = (int)blockIdx.x - c_lo;
+        slots_per_tile = p.sk_slots;
+      } else {
+        sharers = p.splits; slot = blockIdx.z; slots_per_tile = p.splits;
       }
+      if (sharers == 1) {
+        store_final();
+      } else {
+        const int tile_id = m_tile * p.n_tiles + pc.n_tile;
+        uint32_t* base = p.ws + (size_t)tile_id * slots_per_tile * (BT * kBlockW);
+        uint32_t* mine = base + (size_t)slot * (BT * kBlockW);
+#pragma unroll
+        for (int j = 0; j < BT; ++j) mine[j * kBlockW + epi_tid] = __float_as_uint(acc[j]);
+        if (splitk_ticket(p.counters, tile_id, sharers, epi_tid, &ctl->is_last)) {
+#pragma unroll
+          for (int j = 0; j < BT; ++j) acc[j] = 0.f;
+          for (int s = 0; s < sharers; ++s) {
+            const uint32_t* src = base + (size_t)s * (BT * kBlockW) + epi_tid;
+#pragma unroll
+            for (int j = 0; j < BT; ++j) acc[j] += __uint_as_float(__ldcg(src + j * kBlockW));
+          }
+          store_final();
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BT; ++j) acc[j] = 0.f;
     }
   } else {
     // ===================== dequant warps 0..7: thread = one weight row of every second raw block =====================
@@ -632,15 +784,21 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     bool fold_zero = false;
     const int nsub_total = (steps_total + 3) / 4;          // operand sub-blocks (64 K elements) with at least one MMA step
-    const int g_first = k_begin / seg_len;
-    const int g_last = (k_begin + steps_total * 16 - 1) / seg_len - g_first;
+    // table column of a 64-element sub-block = its scale group counted from the CTA's first one; under stream-K every
+    // piece starts on a raw-block (= group) boundary, so the count simply runs on across pieces
+    const int sub_first = p.sk_ctas > 0 ? 0 : k_begin / 64;
+    const int g_first = p.sk_ctas > 0 ? 0 : k_begin / seg_len;
+    const int g_last = (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len;
     if (QK == Q_INT4) {
       asm volatile("bar.sync 4, 384;" ::: "memory");        // zero-point table (written by the epilogue threads) + flag
       fold_zero = ctl->need_xsum == 0;
     }
     if (tl && warp == 0 && lane == 0) tl[kTlMisc + 4] = clock64();
+    // ring position of this group's next raw block, advanced by 2 per iteration (ring depths are even, so no
+    // integer division -- it cost ~30 ALU-pipe instructions per raw block on the pipe that bounds this kernel)
+    int rstage = half;
+    uint32_t rphase = 0;
     for (int rb = half; rb < nrb; rb += 2) {
-      const int rstage = rb % p.w_stages;
       // zero points of this block's four 64-element sub-blocks (each lies in one scale group); fetched before
       // the barrier waits so that the table latency is off the conversion's critical path
       __half2 adds[4];
@@ -649,14 +807,14 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int sub = 0; sub < 4; ++sub) {
           float z = 0.f;
           if (fold_zero) {
-            int g = ((kb0 + rb * 4 + sub) >> p.seg_shift) - g_first;
+            int g = ((sub_first + rb * 4 + sub) >> p.seg_shift) - g_first;
             g = g < g_last ? g : g_last;                     // blocks past K are multiplied by zero activations
             z = lds_f32(zero_tab + row * tab_pitch + g);
           }
           adds[sub] = __floats2half2_rn(-1024.f - z, -64.f - z);
         }
       }
-      mbar_wait(&ctl->w_full[rstage], (rb / p.w_stages) & 1);
+      qwait(&ctl->w_full[rstage], rphase, p.debug);
       const uint8_t* rawrow = w_ring + (size_t)rstage * kABytes + row * 128;
       uint4 raw[8];                                          // the row's 128 raw bytes (8 swizzled 16-byte chunks)
 #pragma unroll
@@ -673,14 +831,37 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int gsub = rb * RW + sub;
         if (gsub < nsub_total) {                               // sub-blocks past the k-range have no MMA step
           const int ostage = gsub % kOpStages;
-          mbar_wait(&ctl->op_empty[ostage], ((gsub / kOpStages) & 1) ^ 1);
+          qwait(&ctl->op_empty[ostage], ((gsub / kOpStages) & 1) ^ 1, p.debug);
           tc_fence_after();
           uint32_t vals[32];
           if (QK == Q_INT4) {
             const uint4 w0 = raw[sub * 2], w1 = raw[sub * 2 + 1];
             const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            if (p.debug & DBG_RAW_OPERAND) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], adds[sub], vals + 4 * j);
+              for (int j = 0; j < 8; ++j) { vals[4 * j] = ws[j]; vals[4 * j + 1] = ws[j] ^ 1u; vals[4 * j + 2] = ws[j] ^ 2u; vals[4 * j + 3] = ws[j] ^ 3u; }
+            } else if (p.debug & DBG_PAIR_K4) {
+              const __half2 mul = __halves2half2(__float2half(1.0f), __float2half(1.0f));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t w8 = ws[j] >> 8;
+                const uint32_t h0 = lop3_and_or(ws[j], 0x000F000Fu, 0x64006400u);
+                const uint32_t h1 = lop3_and_or(ws[j], 0x00F000F0u, 0x64006400u);
+                const uint32_t h2 = lop3_and_or(w8, 0x000F000Fu, 0x64006400u);
+                const uint32_t h3 = lop3_and_or(w8, 0x00F000F0u, 0x64006400u);
+                const __half2 v0 = __hfma2(*reinterpret_cast<const __half2*>(&h0), mul, adds[sub]);
+                const __half2 v1 = __hfma2(*reinterpret_cast<const __half2*>(&h1), mul, adds[sub]);
+                const __half2 v2 = __hfma2(*reinterpret_cast<const __half2*>(&h2), mul, adds[sub]);
+                const __half2 v3 = __hfma2(*reinterpret_cast<const __half2*>(&h3), mul, adds[sub]);
+                vals[4 * j] = *reinterpret_cast<const uint32_t*>(&v0);
+                vals[4 * j + 1] = *reinterpret_cast<const uint32_t*>(&v1);
+                vals[4 * j + 2] = *reinterpret_cast<const uint32_t*>(&v2);
+                vals[4 * j + 3] = *reinterpret_cast<const uint32_t*>(&v3);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], adds[sub], vals + 4 * j);
+            }
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -696,7 +877,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
           }
-          tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 32, vals);
+          if (!(p.debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 32, vals);
+          else asm volatile("" ::"r"(vals[0] ^ vals[7] ^ vals[13] ^ vals[31]));
           pending = ostage;
         }
       }
@@ -707,19 +889,33 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
       }
       if (quad == 0) TL_STAMP(TL_DQ_DONE, rb);
+      rstage += 2;
+      if (rstage >= p.w_stages) { rstage -= p.w_stages; rphase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (tl && threadIdx.x == 0) tl[kTlMisc + 6] = clock64();
+  if (p.timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.timeline[kTlCta + 3 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == kWarpMma0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-static long long* g_timeline = nullptr;   // set through b2l_debug_set_timeline (tools/timeline.py)
-static int g_debug = 0;
 
-constexpr int kMaxGroupsCta = 40;   // scale-table rows per CTA (x 128 rows x 4 B, twice for int4)
+constexpr int kMaxGroupsCta = 40;   // scale-table columns per CTA (x 128 rows x 4 B, twice for int4): tile x split grid
+constexpr int kMaxGroupsSk = 64;    //   ... under stream-K (a CTA's range is sized by bytes, not by groups)
+static int g_streamk = -1;          // env B2L_STREAMK=0 keeps the tile x split grid (A/B measurements)
+static inline bool streamk_enabled() {
+  if (g_streamk < 0) {
+    const char* e = getenv("B2L_STREAMK");
+    g_streamk = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_streamk != 0;
+}
 
 static inline int groups_touched(int kb_per_split, int seg_len) {
   // worst case over split offsets: a k-range of kb_per_split*64 elements starting anywhere on a 64 boundary
@@ -727,40 +923,14 @@ static inline int groups_touched(int kb_per_split, int seg_len) {
   return ((span + seg_len - 1) / seg_len + 1 + 3) / 4 * 4;   // table pitch: whole 16-byte chunks
 }
 
-static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int seg_len) {
-  // token tile capped at 64: the epilogue keeps the running fp32 accumulator in registers
-  SplitPlan pl;
-  const int64_t mt = M > 64 ? 64 : M;
-  pl.bt = pick_bt(mt);
-  pl.n_tiles = (int)cdiv64(N, kBlockW);
-  pl.m_tiles = (int)cdiv64(M, pl.bt);
-  pl.num_kb = (int)cdiv64(K, 64);
-  const int tiles = pl.n_tiles * pl.m_tiles;
-  const int sms = b2l_num_sms();
-  int splits = 1;
-  if (tiles < sms) {
-    splits = sms / tiles;
-    int max_splits = pl.num_kb / 8;
-    if (max_splits < 1) max_splits = 1;
-    if (splits > max_splits) splits = max_splits;
-    if (splits > 32) splits = 32;
-  }
-  const int rw = qk == Q_INT4 ? 4 : 2;     // k-blocks per raw stage: splits must start on a raw-block boundary
-  pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
-  // keep the per-CTA scale table bounded: more splits when groups are fine-grained -- but keep them BALANCED
-  // (equal k-ranges), an uneven last split would make one CTA of every tile the straggler
-  while (pl.kb_per_split > rw && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) {
-    ++splits;
-    pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
-  }
-  pl.splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;
-  const int max_groups = groups_touched(pl.kb_per_split, seg_len);
-  // ring depths: activation blocks (L2-resident, held until their MMAs retire) get the smaller share, the raw
-  // weight ring (HBM latency x bandwidth) everything that is left
+// ring depths + shared-memory footprint for a CTA that processes `blocks` raw blocks and keeps `max_groups` table columns
+static inline void quant_rings(int qk, SplitPlan& pl, int blocks, int max_groups) {
+  const int rw = qk == Q_INT4 ? 4 : 2;
+  // activation blocks (L2-resident, held until their MMAs retire) get the smaller share, the raw weight ring
+  // (HBM latency x bandwidth) everything that is left
   const int x_stage = rw * pl.bt * kStageKBytes;
   const int fixed = 1024 + 1024 + 1024 /*xsum exchange*/ + max_groups * kBlockW * 4 * (qk == Q_INT4 ? 2 : 1);
   const int budget = b2l_max_smem_optin() - fixed;
-  const int blocks = pl.kb_per_split / rw;
   int xs = 4, wsn;
   while (xs > 2 && budget - xs * x_stage < 3 * kABytes) --xs;
   if (xs > blocks + 1) xs = blocks + 1;
@@ -779,6 +949,66 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
   pl.stages = wsn;
   pl.x_stages = xs;
   pl.smem_bytes = fixed + wsn * kABytes + xs * x_stage;
+  pl.max_groups = max_groups;
+}
+
+static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int seg_len) {
+  // token tile capped at 64: the epilogue keeps the running fp32 accumulator in registers
+  SplitPlan pl;
+  const int64_t mt = M > 64 ? 64 : M;
+  pl.bt = pick_bt(mt);
+  pl.n_tiles = (int)cdiv64(N, kBlockW);
+  pl.m_tiles = (int)cdiv64(M, pl.bt);
+  pl.num_kb = (int)cdiv64(K, 64);
+  const int tiles = pl.n_tiles * pl.m_tiles;
+  const int sms = b2l_num_sms();
+  // ---- stream-K: one CTA per SM, equal contiguous shares of the (tile, raw block) space ----
+  {
+    const int raw_k = qk == Q_INT4 ? 256 : 128;
+    const bool aligned = raw_k % seg_len == 0 && raw_k / seg_len <= 2;     // same rule as QuantParams::aligned
+    if (streamk_enabled() && !(g_debug & DBG_NO_STREAMK) && aligned && K % raw_k == 0 && pl.m_tiles == 1) {
+      const int nrb_tile = (int)(K / raw_k);
+      const int64_t total = (int64_t)pl.n_tiles * nrb_tile;
+      int ctas = (int)(total / 2 < sms ? total / 2 : sms);                 // at least two raw blocks per CTA
+      if (ctas < 1) ctas = 1;
+      const int per_cta = (int)((total + ctas - 1) / ctas);
+      const int groups = (per_cta * (raw_k / seg_len) + 3) / 4 * 4;
+      if (groups <= kMaxGroupsSk) {
+        pl.sk_ctas = ctas;
+        pl.nrb_tile = nrb_tile;
+        // most CTAs that can share one tile: a tile's nrb_tile blocks cut by ranges of >= floor(total/ctas) blocks
+        int slots = 1;
+        for (int t = 0; t < pl.n_tiles; ++t) {
+          const int64_t lo = (((int64_t)t * nrb_tile + 1) * ctas - 1) / total;
+          const int64_t hi = (((int64_t)(t + 1) * nrb_tile) * ctas - 1) / total;
+          if ((int)(hi - lo + 1) > slots) slots = (int)(hi - lo + 1);
+        }
+        pl.sk_slots = slots;
+        pl.splits = slots > 1 ? slots : 1;       // "needs workspace" for the callers that only look at splits
+        pl.kb_per_split = pl.num_kb;
+        quant_rings(qk, pl, per_cta, groups);
+        return pl;
+      }
+    }
+  }
+  int splits = 1;
+  if (tiles < sms) {
+    splits = sms / tiles;
+    int max_splits = pl.num_kb / 8;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 32) splits = 32;
+  }
+  const int rw = qk == Q_INT4 ? 4 : 2;     // k-blocks per raw stage: splits must start on a raw-block boundary
+  pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
+  // keep the per-CTA scale table bounded: more splits when groups are fine-grained -- but keep them BALANCED
+  // (equal k-ranges), an uneven last split would make one CTA of every tile the straggler
+  while (pl.kb_per_split > rw && groups_touched(pl.kb_per_split, seg_len) > kMaxGroupsCta) {
+    ++splits;
+    pl.kb_per_split = ((pl.num_kb + splits - 1) / splits + rw - 1) / rw * rw;
+  }
+  pl.splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+  quant_rings(qk, pl, pl.kb_per_split / rw, groups_touched(pl.kb_per_split, seg_len));
   return pl;
 }
 
@@ -792,6 +1022,7 @@ static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const Quant
     configured_smem = pl.smem_bytes;
   }
   dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.m_tiles, (unsigned)pl.splits);
+  if (pl.sk_ctas > 0) grid = dim3((unsigned)pl.sk_ctas, (unsigned)pl.m_tiles, 1);
   b2l_launch(kern, dim3(grid), dim3(kQuantThreads), (size_t)(pl.smem_bytes), st, tw, tx, p);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
@@ -812,9 +1043,11 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
                         int64_t y_row_stride, void* workspace, int64_t workspace_bytes, void* counters,
                         int64_t num_counters, CUtensorMap* tw, CUtensorMap* tx, const char* what, int seg_len) {
   pl = quant_plan(qk, m, n, k, seg_len);
-  p.max_groups = groups_touched(pl.kb_per_split, seg_len);
+  p.max_groups = pl.max_groups;
+  p.sk_ctas = pl.sk_ctas; p.sk_slots = pl.sk_slots; p.nrb_tile = pl.nrb_tile; p.n_tiles = pl.n_tiles;
   p.y = y; p.ldy = y_row_stride; p.M = (int)m; p.N = (int)n; p.K = (int)k;
   p.splits = pl.splits; p.kb_per_split = pl.kb_per_split; p.num_kb = pl.num_kb; p.w_stages = pl.stages; p.x_stages = pl.x_stages;
+  if ((g_debug & DBG_HALF_RING) && p.w_stages >= 4) p.w_stages = (p.w_stages / 2) & ~1;
   p.timeline = g_timeline;
   p.debug = g_debug;
   p.x = x; p.ldx = x_row_stride;
@@ -878,6 +1111,17 @@ extern "C" int64_t b2l_quant_gemm_workspace_bytes(int kind, int64_t m, int64_t n
   if (pl.splits <= 1) return 0;
   return (int64_t)pl.n_tiles * pl.m_tiles * pl.splits * pl.bt * kBlockW * 4;
 }
+// Launch plan of a quantised GEMM (pure function of shapes and the SM count; no GPU work):
+// out[0..9] = {stream-K CTAs (0 = tile x split grid), workspace slots per tile, raw blocks per tile, weight-row tiles,
+//              splits, 64-element k-blocks per split, weight ring depth, activation ring depth, smem bytes, table columns}
+extern "C" int b2l_quant_gemm_plan(int kind, int64_t m, int64_t n, int64_t k, int64_t group_k, int* out, void* /*reserved*/) {
+  B2L_REQUIRE(out && m > 0 && n > 0 && k > 0 && group_k > 0, "quant_gemm_plan: bad arguments");
+  const SplitPlan pl = quant_plan(kind, m, n, k, seg_len_for(kind, k, group_k));
+  out[0] = pl.sk_ctas; out[1] = pl.sk_slots; out[2] = pl.nrb_tile; out[3] = pl.n_tiles; out[4] = pl.splits;
+  out[5] = pl.kb_per_split; out[6] = pl.stages; out[7] = pl.x_stages; out[8] = pl.smem_bytes; out[9] = pl.max_groups;
+  return B2L_OK;
+}
+
 extern "C" int64_t b2l_quant_gemm_num_counters(int64_t m, int64_t n) {
   if (m <= 0 || n <= 0) return 0;
   return cdiv64(n, kBlockW) * cdiv64(m, pick_bt(m > 64 ? 64 : m));

@@ -37,6 +37,10 @@ struct SplitPlan {
   int stages;
   int x_stages;       // quantised GEMMs: depth of the separate activation ring
   int smem_bytes;
+  int sk_ctas = 0;    // quantised GEMMs: stream-K CTA count (0 = tile x split grid)
+  int sk_slots = 0;   //   workspace slots per tile under stream-K
+  int nrb_tile = 0;   //   raw blocks per tile
+  int max_groups = 0; //   scale-table columns per CTA
 };
 
 static inline int pick_bt(int64_t m) {

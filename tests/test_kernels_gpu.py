@@ -667,3 +667,82 @@ def test_pdl_kernel_chain_llama_shapes_bit_identical():
     assert torch.isfinite(a[0].float()).all()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert torch.equal(b[0], c[0])
+
+
+# --------------------------------------------------------------------------- #
+# stream-K schedule of the quantised GEMMs (csrc/gemm_quant.cu): CTA ranges that start and end inside tiles
+# --------------------------------------------------------------------------- #
+def _plan(kind, m, n, k, gk):
+    import ctypes
+
+    from lite_llama_b200 import _lib
+
+    out = (ctypes.c_int * 10)()
+    _lib.check(_lib.load().b2l_quant_gemm_plan(kind, m, n, k, gk, out, None))
+    return list(out)
+
+
+@pytest.mark.parametrize("m,n,k", [(16, 640, 1792), (3, 130, 768), (32, 1000, 2304), (64, 384, 4096), (7, 128, 5120)])
+def test_w4a16_stream_k_piece_boundaries(m, n, k):
+    # tile counts and K depths chosen so that CTA ranges cut tiles at odd places, several CTAs share a tile and one
+    # CTA spans up to three tiles; N not a multiple of 128 puts rows past N into the last tile
+    gs = 128
+    assert _plan(0, m, n, k, gs)[0] > 0, "shape is expected to take the stream-K schedule"
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k, dtype=torch.float32) * 0.05
+    qw, sc, zp = ops.quantize_int4_groupwise(w, gs)
+    bias = torch.randn(n)
+    args = (x, qw.cuda(), sc.cuda(), zp.cuda())
+    out = K().w4a16_matmul(*args, group_size=gs, bias=bias.cuda())
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs, bias), **GEMM_TOL)
+    for _ in range(3):   # partial sums are combined in CTA order, whoever finishes last: bit-stable
+        assert torch.equal(out, K().w4a16_matmul(*args, group_size=gs, bias=bias.cuda()))
+
+
+def test_w4a16_stream_k_group_256_and_fractional_zero_points():
+    m, n, k, gs = 9, 384, 2048, 256
+    assert _plan(0, m, n, k, gs)[0] > 0
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), dtype=torch.int64).to(torch.int32)
+    sc = torch.rand(n, k // gs) * 0.01 + 0.001
+    zp = torch.randint(0, 16, (n, k // gs)).float()
+    out = K().w4a16_matmul(x, qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs)
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs), **GEMM_TOL)
+    zp[200, 3] += 0.25      # one fractional zero point: the CTAs that hold it switch to the row-sum correction
+    out = K().w4a16_matmul(x, qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs)
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs), **GEMM_TOL)
+
+
+@pytest.mark.parametrize("m,n,k", [(5, 640, 1152), (32, 2048, 2048), (64, 300, 896)])
+def test_w8a16_stream_k_block_scales(m, n, k):
+    assert _plan(1, m, n, k, 128)[0] > 0
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k) * 0.05
+    qw = w.to(torch.float8_e4m3fn).view(torch.uint8)
+    sc = torch.rand((n + 127) // 128, (k + 127) // 128) + 0.5
+    bias = torch.randn(n, dtype=torch.float16)
+    out = K().w8a16_matmul(x, qw.cuda(), sc.cuda(), group_n=128, group_k=128, bias=bias.cuda())
+    close(out, ops.w8a16_matmul(x.cpu(), qw, sc, 128, 128, bias), **GEMM_TOL)
+    qi = torch.randint(-127, 128, (n, k), dtype=torch.int8)
+    si = torch.rand((n + 63) // 64, (k + 127) // 128) * 0.01
+    out = K().w8a16_matmul(x, qi.cuda(), si.cuda(), group_n=64, group_k=128)
+    close(out, ops.w8a16_matmul(x.cpu(), qi, si, 64, 128), **GEMM_TOL)
+
+
+@pytest.mark.parametrize("n,k", [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)])
+@pytest.mark.parametrize("m", [1, 32])
+def test_w4a16_llama3_8b_projection_shapes(m, n, k):
+    # full BASELINE shapes: compared on the GPU with an fp32 matmul over the dequantised weights (same formula as
+    # oracle/ops.py:w4a16_matmul, which takes minutes at this size on the CPU)
+    gs = 128
+    torch.manual_seed(1)
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), device="cuda", dtype=torch.int64).to(torch.int32)
+    sc = torch.rand(n, k // gs, device="cuda") * 0.004 + 0.001
+    zp = torch.randint(0, 16, (n, k // gs), device="cuda").float()
+    out = K().w4a16_matmul(x, qw, sc, zp, group_size=gs)
+    shifts = torch.arange(8, device="cuda", dtype=torch.int32) * 4
+    nib = ((qw.unsqueeze(-1) >> shifts) & 0xF).reshape(n, k).float()
+    wd = (nib - zp.repeat_interleave(gs, dim=1)) * sc.repeat_interleave(gs, dim=1)
+    ref = x.float() @ wd.T
+    torch.testing.assert_close(out.float(), ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()))

@@ -46,6 +46,12 @@ for step in $STEPS; do
     bench_nopdl)
       B2L_PDL=0 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_nopdl.json 2> gpurun_out/bench_nopdl.err
       echo "bench_nopdl exit=$?" >> $S; tail -3 gpurun_out/bench_nopdl.err >> $S ;;
+    bench_nosk)
+      B2L_STREAMK=0 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_nosk.json 2> gpurun_out/bench_nosk.err
+      echo "bench_nosk exit=$?" >> $S; tail -3 gpurun_out/bench_nosk.err >> $S ;;
+    probe)
+      timeout 300 python tools/qgemm_probe.py > gpurun_out/qgemm_probe.jsonl 2> gpurun_out/qgemm_probe.err
+      echo "probe exit=$?" >> $S; tail -3 gpurun_out/qgemm_probe.err >> $S ;;
     micro)
       timeout 300 python tools/microbench.py > gpurun_out/microbench.jsonl 2> gpurun_out/microbench.err
       echo "micro exit=$?" >> $S ;;

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--n", type=int, default=28672)
     ap.add_argument("--k", type=int, default=4096)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--hot", type=int, default=0, help="launches issued right before the stamped one (sustained-load clocks)")
+    ap.add_argument("--brief", action="store_true")
     a = ap.parse_args()
     lib = _lib.load()
     lib.b2l_debug_set_timeline.argtypes = [ctypes.c_void_p]
@@ -31,10 +33,18 @@ def main():
     dev = "cuda"
     x = torch.randn(a.m, a.k, device=dev, dtype=torch.float16) * 0.5
     if a.op == "w4a16":
-        qw = torch.randint(-(2**31), 2**31 - 1, (a.n, a.k // 8), device=dev, dtype=torch.int64).to(torch.int32)
-        sc = torch.rand(a.n, a.k // 128, device=dev) * 0.01
-        zp = torch.full((a.n, a.k // 128), 8.0, device=dev)
-        fn = lambda: K.w4a16_matmul(x, qw, sc, zp, group_size=128)
+        sets = []
+        for _ in range(4 if a.hot else 1):   # hot mode cycles through 4 weight sets so that no launch finds its weights in L2
+            qw = torch.randint(-(2**31), 2**31 - 1, (a.n, a.k // 8), device=dev, dtype=torch.int64).to(torch.int32)
+            sc = torch.rand(a.n, a.k // 128, device=dev) * 0.01
+            zp = torch.full((a.n, a.k // 128), 8.0, device=dev)
+            sets.append((qw, sc, zp))
+        calls = [0]
+
+        def fn():
+            qw, sc, zp = sets[calls[0] % len(sets)]
+            calls[0] += 1
+            return K.w4a16_matmul(x, qw, sc, zp, group_size=128)
     else:
         qw = torch.randint(0, 120, (a.n, a.k), device=dev, dtype=torch.uint8)
         sc = torch.rand((a.n + 127) // 128, (a.k + 127) // 128, device=dev)
@@ -42,17 +52,36 @@ def main():
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    tl = torch.zeros(16 * 256, dtype=torch.int64, device=dev)
+    tl = torch.zeros(16 * 256 + 3 * 1024, dtype=torch.int64, device=dev)
     lib.b2l_debug_set_flags(a.flags)
-    lib.b2l_debug_set_timeline(tl.data_ptr())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     flush.zero_()
+    for _ in range(a.hot):
+        fn()
+    lib.b2l_debug_set_timeline(tl.data_ptr())
     fn()
     torch.cuda.synchronize()
     lib.b2l_debug_set_timeline(None)
     lib.b2l_debug_set_flags(0)
-    steps = tl.cpu()[2048:].view(128, 16)
+    cta = tl.cpu()[4096:].view(1024, 3)
+    steps = tl.cpu()[2048:4096].view(128, 16)
     t = tl.cpu()[:2048].view(8, 256)
+    live = cta[:, 0] > 0
+    if bool(live.any()):
+        st, en, sm = cta[live, 0], cta[live, 1], cta[live, 2]
+        g0 = int(st.min())
+        dur = (en - st).float()
+        print(f"== {a.op} m={a.m} n={a.n} k={a.k} flags={a.flags} hot={a.hot}: {int(live.sum())} CTAs, kernel wall {int(en.max()) - g0} ns; "
+              f"CTA start spread {int(st.max()) - g0} ns; CTA duration min/median/max {int(dur.min())}/{int(dur.median())}/{int(dur.max())} ns; "
+              f"last exit by CTA {int(en.argmax())} on SM {int(sm[en.argmax()])}")
+        m6, m0_ = int(tl.cpu()[3072 + 6]), int(tl.cpu()[3072])
+        if m6 > 0 and int(cta[0, 1]) > int(cta[0, 0]):
+            print(f"   CTA 0: {m6 - m0_} cycles in {int(cta[0,1]) - int(cta[0,0])} ns -> SM clock {(m6 - m0_) / (int(cta[0,1]) - int(cta[0,0])):.3f} GHz")
+        order = torch.argsort(en - g0)
+        print("   slowest exits (cta: start,end ns):", [(int(i), int(st[i]) - g0, int(en[i]) - g0) for i in order[-5:]])
+        print("   fastest exits:", [(int(i), int(st[i]) - g0, int(en[i]) - g0) for i in order[:3]])
+    if a.brief:
+        return
     names = ["PROD", "MMA_READY", "MMA_ISSUED", "DQ_START", "DQ_DONE", "EPI_START", "EPI_DONE"]
     t0 = int(t[t > 0].min())
     print(f"== {a.op} m={a.m} n={a.n} k={a.k}: total cycles {int(t[t>0].max()) - t0}")
