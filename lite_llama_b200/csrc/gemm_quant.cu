@@ -41,8 +41,9 @@ constexpr int kQuantThreads = 16 * 32;      // 2 x 4 dequant warps, 4 epilogue, 
 // slot behind the dequant warps of their sub-partition.  warp % 4 = TMEM lane quadrant for dequant / epilogue.
 constexpr int kWarpEpi0 = 8;                // epilogue warps 8..11
 constexpr int kWarpXProd = 12, kWarpWProd = 13, kWarpMma1 = 14, kWarpMma0 = 15;
-constexpr int kOpStages = 8;                // TMEM operand sub-stages (64 K elements = 32 columns each)
+constexpr int kMaxOpStages = 12;            // TMEM operand sub-stages (64 K elements = 32 columns each): template parameter OPS
 constexpr int kMaxRawStages = 8;
+constexpr int kTabPitch = 129;            // floats per scale-table column (128 weight rows + 1: conflict-free both ways)
 
 enum QuantKind { Q_INT4 = 0, Q_FP8 = 1, Q_INT8 = 2 };
 
@@ -68,6 +69,7 @@ struct QuantParams {
   int w_stages, x_stages;                  // ring depths: raw weight blocks / activation blocks
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
   int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
+  int subwait;                             // MMA warps wait per 64-element sub-block (1) or per whole segment (0)
   long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
   int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
@@ -78,7 +80,8 @@ struct QuantParams {
 enum { DBG_FORCE_XSUM = 8, DBG_RAW_OPERAND = 16, DBG_PAIR_K4 = 32, DBG_NO_STREAMK = 64, DBG_SKIP_DRAIN = 128,
        DBG_FEW_MMA = 256 /* issue 1 of every 4 MMAs */, DBG_NO_STTM = 512 /* skip the TMEM operand store */,
        DBG_WAIT_SPIN = 1024 /* mbarrier.test_wait polling */, DBG_WAIT_SHORT = 2048 /* try_wait without the long suspend hint */,
-       DBG_NO_XLOAD = 4096 /* activation tiles are never fetched */, DBG_HALF_RING = 8192 /* half the weight ring depth */ };
+       DBG_NO_XLOAD = 4096 /* activation tiles are never fetched */, DBG_HALF_RING = 8192 /* half the weight ring depth */,
+       DBG_FORCE = 32768 /* no experiment: just run the DBG instantiation (prices its code size) */ };
 __device__ __forceinline__ void qwait(uint64_t* bar, uint32_t parity, int debug) {
   if (debug & DBG_WAIT_SPIN) mbar_wait_spin(bar, parity);
   else if (debug & DBG_WAIT_SHORT) mbar_wait_short(bar, parity);
@@ -102,11 +105,10 @@ struct __align__(8) QControl {
   uint64_t w_empty[kMaxRawStages];
   uint64_t x_full[kMaxRawStages];
   uint64_t x_empty[kMaxRawStages];
-  uint64_t op_full[kOpStages];
-  uint64_t op_empty[kOpStages];
+  uint64_t op_full[kMaxOpStages];
+  uint64_t op_empty[kMaxOpStages];
   uint64_t acc_full[4];
   uint64_t acc_empty[4];
-  int need_xsum;                           // int4: some zero point of this CTA is not an integer in [0, 1023]
   uint32_t tmem_base;
   int is_last;
 };
@@ -259,9 +261,10 @@ __device__ __forceinline__ void st_release_smem(int* p, int v) {
 // (scale group divides the raw block).  Everything but the stage addresses is a compile-time constant, so the
 // elected lane runs a straight line of UTCHMMA/UTCBAR; a device timeline showed that ~40 bookkeeping
 // instructions per step in the generic loop cost 160 cycles per MMA against 16 cycles of tensor-pipe time.
-template <int QK, int BT, int SEG_STEPS>
+template <int QK, int BT, int OPS, int SEG_STEPS>
 __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_base, uint32_t a_base, uint64_t bdesc0,
-                                                int seg0, int gsub0, uint64_t* x_empty, long long* tl, int debug = 0) {
+                                                int seg0, int gsub0, uint64_t* x_empty, long long* tl, int debug, int subwait) {
+  constexpr int kOpStages = OPS;
   constexpr int RW = raw_sub<QK>();
   constexpr int NSEG = RW * 4 / SEG_STEPS;
   constexpr int SPS = SEG_STEPS / 4;              // operand sub-blocks per segment
@@ -272,8 +275,36 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
   for (int s = 0; s < NSEG; ++s) {
     const int seg = seg0 + s;
     const int buf = seg & (NB - 1);
+    const uint32_t d = tmem_base + buf * BT;
     // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
     qwait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1, debug);
+    if (subwait) {
+      // issue each 64-element sub-block as soon as ITS operand stage is full: the dequant warps run one sub-block
+      // ahead of the tensor pipe instead of a whole segment ahead
+#pragma unroll
+      for (int q = 0; q < SPS; ++q) {
+        const int gsub = gsub0 + s * SPS + q;
+        const int ostage = gsub % kOpStages;
+        qwait(&ctl->op_full[ostage], (gsub / kOpStages) & 1, debug);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int st = (s * SPS + q) * 4 + j;
+            if (!(debug & DBG_FEW_MMA) || j == 3)
+              umma_f16_ts(d, a_base + ostage * 32 + j * 8,
+                          bdesc0 + (uint64_t)((((st >> 2) * kXBytes) >> 4) + 2 * j), idesc, (q > 0 || j > 0) ? 1u : 0u);
+          }
+          tc_commit(&ctl->op_empty[ostage]);
+          if (q == SPS - 1) {
+            tc_commit(&ctl->acc_full[buf]);
+            if (s == NSEG - 1) tc_commit(x_empty);
+          }
+        }
+        __syncwarp();
+      }
+      continue;
+    }
 #pragma unroll
     for (int q = 0; q < SPS; ++q) {
       const int gsub = gsub0 + s * SPS + q;
@@ -282,7 +313,6 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
     tc_fence_after();
     if (tl && seg < 128 && (threadIdx.x & 31) == 0) tl[2048 + seg * 2] = clock64();
     if (elect_one()) {
-      const uint32_t d = tmem_base + buf * BT;
 #pragma unroll
       for (int j = 0; j < SEG_STEPS; ++j) {
         const int st = s * SEG_STEPS + j;
@@ -300,11 +330,16 @@ __device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_bas
   }
 }
 
-template <int QK, int BT>
+template <int QK, int BT, int OPS, bool DBG>
 __global__ void __launch_bounds__(kQuantThreads, 1)
 gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const QuantParams p) {
   using T = __half;
+  constexpr int kOpStages = OPS;
+  // the debug experiments and the timeline stamps only exist in the DBG instantiation (selected by the host when a
+  // debug flag or a timeline buffer is set): the product kernel carries none of their code
+  const int debug = DBG ? p.debug : 0;
+  long long* const timeline = DBG ? p.timeline : nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   QControl* ctl = reinterpret_cast<QControl*>(smem);
@@ -318,12 +353,14 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   constexpr int kRawK = RW * 64;
   constexpr int kXStage = RW * kXBytes;
   uint8_t* x_ring = w_ring + (size_t)p.w_stages * kABytes;
-  // per-row scale (and zero-point) table of this CTA's k-range, row-major [128 rows][tab_pitch] fp32, filled
-  // once with cp.async by the epilogue threads (each thread only touches its own row -> no barrier needed)
+  // scale (and zero-point) table of this CTA's k-range, TRANSPOSED: [scale group][kTabPitch = 129] fp32 with the weight
+  // row as the fast index, so that the row-per-thread readers (dequant, epilogue) are bank-conflict free.  (The first
+  // layout, row-major with one cp.async stream per row, made every access a 32-way bank conflict and took 5000
+  // cycles just to issue: ncu + device timeline under profiles/.)
   float* scale_tab = reinterpret_cast<float*>(x_ring + (size_t)p.x_stages * kXStage);
-  const int tab_pitch = p.max_groups;                  // multiple of 4 floats
-  float* zero_tab = scale_tab + (size_t)tab_pitch * kBlockW;
-  float* xs_smem = zero_tab + (QK == Q_INT4 ? (size_t)tab_pitch * kBlockW : 0);   // [2][BT] per-segment xsum exchange
+  const int tab_floats = (p.max_groups * kTabPitch + 3) & ~3;
+  float* zero_tab = scale_tab + tab_floats;
+  float* xs_smem = zero_tab + (QK == Q_INT4 ? tab_floats : 0);   // [2][BT] per-segment xsum exchange
   // TMEM map (columns): [NB accumulator buffers of BT] [kOpStages operand sub-stages of 32]
   constexpr int NB = 4;
   constexpr int kAColBase = NB * BT;
@@ -334,7 +371,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.y;
-  long long* tl = (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.timeline : nullptr;
+  long long* tl = (timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? timeline : nullptr;
   const int seg_len = p.group_k;                  // K elements per scale group (multiple of 16)
   // ---- this CTA's work: pieces (tile, raw-block range); see struct Piece ----
   WorkRange wr;
@@ -372,129 +409,168 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (tl && threadIdx.x == 0) tl[kTlMisc + 0] = clock64();
   // every CTA: wall-clock (globaltimer, ns) at entry and exit + its SM id -> who is the straggler, and what is the
   // real SM clock (CTA 0 also stamps clock64 at both ends)
-  if (p.timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
+  if (timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
     unsigned long long gt; unsigned smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.timeline[kTlCta + 3 * blockIdx.x] = (long long)gt;
-    p.timeline[kTlCta + 3 * blockIdx.x + 2] = (long long)smid;
+    timeline[kTlCta + 3 * blockIdx.x] = (long long)gt;
+    timeline[kTlCta + 3 * blockIdx.x + 2] = (long long)smid;
   }
 
-  if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
-    // Stage this CTA's scale / zero-point rows FIRST: the dequant warps cannot convert a single weight before the
-    // zero points are here, and a request issued after the weight ring's TMA loads queues behind 128 KiB per SM
-    // of weight traffic (ncu: the dequant warps spent a quarter of the CTA's life at the start-up barrier).
-    // Each epilogue thread copies -- and later reads back -- only its own row, so no barrier is involved;
-    // 16 bytes (4 groups) per cp.async when the row is contiguous and aligned.  The tables are weights (static),
-    // so this runs before griddepcontrol.wait.
-    const int epi_tid = (warp & 3) * 32 + lane;
-    float* sdst = scale_tab + epi_tid * tab_pitch;
-    float* zdst = zero_tab + epi_tid * tab_pitch;
-    int tcol = 0;                                            // table column = scale group, linear over the pieces
-    for (int pi = 0; pi < wr.npieces; ++pi) {
-      const Piece pc = wr.piece(pi);
-      const int n = pc.n_tile * kBlockW + epi_tid;
-      int g_first, g_count;
-      if (p.sk_ctas > 0) {
-        g_first = pc.rb_lo * kRawK / seg_len;
-        g_count = (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
-      } else {
-        g_first = k_begin / seg_len;
-        g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
-      }
-      if (n < p.N) {
-        const float* srow = p.scales + (int64_t)(n / p.group_n) * p.s_stride_n + (int64_t)g_first * p.s_stride_k;
-        const float* zrow = QK == Q_INT4 ? p.zeros + (int64_t)n * p.s_stride_n + (int64_t)g_first * p.s_stride_k : nullptr;
-        // widest copy both sides allow (source and destination columns may differ in alignment under stream-K)
-        int w = 1;
-        if (p.s_stride_k == 1) {
-          const uintptr_t a = (uintptr_t)srow | (uintptr_t)(sdst + tcol) | (QK == Q_INT4 ? ((uintptr_t)zrow | (uintptr_t)(zdst + tcol)) : 0);
-          w = (a % 16 == 0) ? 4 : (a % 8 == 0) ? 2 : 1;
-        }
-        int g = 0;
-        // zero points first: they gate the dequant warps, the scales are only needed by the first drain
-        if (w == 4) {
-          if (QK == Q_INT4)
-            for (int gz = 0; gz + 4 <= g_count; gz += 4)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(zdst + tcol + gz)), "l"(zrow + gz) : "memory");
-          for (; g + 4 <= g_count; g += 4)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + tcol + g)), "l"(srow + g) : "memory");
-        } else if (w == 2) {
-          if (QK == Q_INT4)
-            for (int gz = 0; gz + 2 <= g_count; gz += 2)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(zdst + tcol + gz)), "l"(zrow + gz) : "memory");
-          for (; g + 2 <= g_count; g += 2)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst + tcol + g)), "l"(srow + g) : "memory");
-        }
-        for (; g < g_count; ++g) {
-          if (QK == Q_INT4)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zdst + tcol + g)),
-                         "l"(zrow + (int64_t)g * p.s_stride_k) : "memory");
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst + tcol + g)),
-                       "l"(srow + (int64_t)g * p.s_stride_k) : "memory");
-        }
-      } else {
-        // rows past N: benign values so that the zero-point check below never trips on garbage
-        for (int g = 0; g < g_count; ++g) { sdst[tcol + g] = 0.f; if (QK == Q_INT4) zdst[tcol + g] = 0.f; }
-      }
-      tcol += g_count;
+  // weight producer state (warp kWarpWProd): the first ring-full of TMA loads is issued BEFORE the set-up barrier
+  PipeState ws(p.w_stages);
+  int w_pi = 0, w_lin = 0;
+  Piece w_pc = wr.piece(0);
+  int w_rb = w_pc.rb_lo;
+  auto w_issue = [&](bool wait) {
+    if (wait) qwait(&ctl->w_empty[ws.stage], ws.phase ^ 1, debug);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&ctl->w_full[ws.stage], kABytes);     // OOB parts are zero-filled but still counted
+      const int kb = w_rb * RW;                                      // first 64-element k-block of this raw block
+      tma_load_2d_hint(w_ring + (size_t)ws.stage * kABytes, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64,
+                       w_pc.n_tile * kBlockW, &ctl->w_full[ws.stage], kEvictFirst);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    __syncwarp();
+    TL_STAMP(TL_PROD, w_lin);
+    ws.advance();
+    ++w_lin;
+    if (++w_rb == w_pc.rb_hi && w_lin < nrb) { w_pc = wr.piece(++w_pi); w_rb = w_pc.rb_lo; }
+  };
+
+  // int4: this thread saw a zero point that cannot be folded (or the group size rules folding out altogether)
+  int bad_zero = (QK == Q_INT4 && (p.force_xsum || (debug & DBG_FORCE_XSUM))) ? 1 : 0;
+  constexpr int kFillWarps = kWarpEpi0 + 4;
+  if (warp < kFillWarps) {
+    // ---- warps 0..11 (idle until the first weights land): stage the scale / zero-point table ----
+    // A lane owns table columns `lane` and `lane + 32` (a CTA keeps at most 64 scale groups: host), warp w copies
+    // rows w, w+12, ...: global reads are coalesced along a weight row's groups and the transposed shared-memory
+    // writes hit 32 different banks.  EVERY load is issued before the first store and before the weight producer
+    // is released (named barrier 5): table requests that queue behind a ring-full of weight traffic per SM took
+    // ~10000 cycles to come back (device timeline, profiles/).  The tables are weights (static), so all of this
+    // runs before griddepcontrol.wait.
+    constexpr int kRowsPerWarp = (kBlockW + kFillWarps - 1) / kFillWarps;
+    int col_tile[2] = {0, 0}, col_g[2] = {0, 0};
+    bool col_ok[2] = {false, false};
+    {
+      int tcol = 0;                                    // table column = scale group, linear over the pieces
+      for (int pi = 0; pi < wr.npieces; ++pi) {
+        const Piece pc = wr.piece(pi);
+        int g_first, g_count;
+        if (p.sk_ctas > 0) {
+          g_first = pc.rb_lo * kRawK / seg_len;
+          g_count = (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
+        } else {
+          g_first = k_begin / seg_len;
+          g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int tc = lane + 32 * h;
+          if (tc >= tcol && tc < tcol + g_count) { col_ok[h] = true; col_tile[h] = pc.n_tile; col_g[h] = g_first + tc - tcol; }
+        }
+        tcol += g_count;
+      }
+    }
+    // branch-free issue: out-of-range elements read element 0 and are zeroed afterwards (rows past N: benign
+    // values); the scale row of weight row n is n / group_n -- a shift for the power-of-two groups in use
+    float sv[kRowsPerWarp][2], zv[kRowsPerWarp][2];
+    const int gn_shift = (p.group_n & (p.group_n - 1)) == 0 ? 31 - __clz(p.group_n) : -1;
+    const float* sbase[2];
+    const float* zbase[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      sbase[h] = p.scales + (int64_t)col_g[h] * p.s_stride_k;
+      zbase[h] = QK == Q_INT4 ? p.zeros + (int64_t)col_g[h] * p.s_stride_k : nullptr;
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+      const int r = warp + i * kFillWarps;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = col_tile[h] * kBlockW + r;
+        const bool ok = col_ok[h] && r < kBlockW && n < p.N;
+        const int sn = QK == Q_INT4 ? n : (gn_shift >= 0 ? (n >> gn_shift) : n / p.group_n);   // int4: group_n = 1
+        sv[i][h] = __ldg(sbase[h] + (int64_t)(ok ? sn : 0) * p.s_stride_n);
+        if (QK == Q_INT4) zv[i][h] = __ldg(zbase[h] + (int64_t)(ok ? n : 0) * p.s_stride_n);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+      const int r = warp + i * kFillWarps;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool ok = col_ok[h] && r < kBlockW && col_tile[h] * kBlockW + r < p.N;
+        if (!ok) { sv[i][h] = 0.f; if (QK == Q_INT4) zv[i][h] = 0.f; }
+      }
+    }
+    asm volatile("bar.arrive 5, %0;" ::"n"((kFillWarps + 1) * 32) : "memory");   // loads are out: release the weight producer
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+      const int r = warp + i * kFillWarps;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int tc = lane + 32 * h;
+        if (col_ok[h] && r < kBlockW) {
+          scale_tab[tc * kTabPitch + r] = sv[i][h];
+          if (QK == Q_INT4) {
+            const float z = zv[i][h];
+            zero_tab[tc * kTabPitch + r] = z;
+            bad_zero |= !(z >= 0.f && z <= 1023.f && z == rintf(z));
+          }
+        }
+      }
+    }
+    if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 7] = clock64();
   }
 
-  if (warp == kWarpWProd && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_x);
-    for (int s = 0; s < p.w_stages; ++s) {
-      mbar_init(&ctl->w_full[s], 1);
-      mbar_init(&ctl->w_empty[s], 4);        // the 4 dequant warps that convert the block
+  if (warp == kWarpWProd) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_w);
+      tma_prefetch_desc(&tmap_x);
+      for (int s = 0; s < p.w_stages; ++s) {
+        mbar_init(&ctl->w_full[s], 1);
+        mbar_init(&ctl->w_empty[s], 4);        // the 4 dequant warps that convert the block
+      }
+      for (int s = 0; s < p.x_stages; ++s) {
+        mbar_init(&ctl->x_full[s], 1);
+        mbar_init(&ctl->x_empty[s], 1);        // tcgen05.commit of the MMA warp that issued the block
+      }
+      for (int s = 0; s < kOpStages; ++s) {
+        mbar_init(&ctl->op_full[s], 4);
+        mbar_init(&ctl->op_empty[s], 1);
+      }
+      for (int s = 0; s < NB; ++s) {
+        mbar_init(&ctl->acc_full[s], 1);
+        mbar_init(&ctl->acc_empty[s], 4);
+      }
+      mbar_fence_init();
+      fence_proxy_async_smem();
+      if (tl) tl[kTlMisc + 8] = clock64();
     }
-    for (int s = 0; s < p.x_stages; ++s) {
-      mbar_init(&ctl->x_full[s], 1);
-      mbar_init(&ctl->x_empty[s], 1);        // tcgen05.commit of the MMA warp that issued the block
-    }
-    for (int s = 0; s < kOpStages; ++s) {
-      mbar_init(&ctl->op_full[s], 4);
-      mbar_init(&ctl->op_empty[s], 1);
-    }
-    for (int s = 0; s < NB; ++s) {
-      mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], 4);
-    }
-    ctl->need_xsum = 0;
-    mbar_fence_init();
+    __syncwarp();
+    // Weights are static: under programmatic dependent launch this stream starts while the previous kernel is
+    // still running (no griddepcontrol.wait on this path) -- and before the rest of the CTA has finished setting up,
+    // but after the table requests are on their way (see above).
+    asm volatile("bar.sync 5, %0;" ::"n"((kFillWarps + 1) * 32) : "memory");
+    const int pre = nrb < p.w_stages ? nrb : p.w_stages;
+    for (int i = 0; i < pre; ++i) w_issue(false);
   }
   if (warp == kWarpMma0) {
     tmem_alloc(&ctl->tmem_base, kTmemCols);
     tmem_relinquish();
+    if (tl && lane == 0) tl[kTlMisc + 9] = clock64();
   }
+  if (tl && threadIdx.x == 0) tl[kTlMisc + 10] = clock64();
   tc_fence_before();
-  __syncthreads();
+  // the set-up barrier also publishes the table and ORs the "zero point cannot be folded" flags of the fill threads
+  const bool cta_need_xsum = __syncthreads_or(bad_zero) != 0;
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   if (tl && threadIdx.x == 0) tl[kTlMisc + 1] = clock64();
 
   if (warp == kWarpWProd) {
     // ===================== weight producer (whole warp loops, one elected lane issues) =====================
-    // Weights are static: under programmatic dependent launch this stream starts while the previous kernel
-    // is still running (no griddepcontrol.wait on this path).
-    PipeState ws(p.w_stages);
-    int lin = 0;
-    for (int pi = 0; pi < wr.npieces; ++pi) {
-      const Piece pc = wr.piece(pi);
-      for (int rb = pc.rb_lo; rb < pc.rb_hi; ++rb, ++lin) {
-        qwait(&ctl->w_empty[ws.stage], ws.phase ^ 1, p.debug);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&ctl->w_full[ws.stage], kABytes);     // OOB parts are zero-filled but still counted
-          const int kb = rb * RW;                                      // first 64-element k-block of this raw block
-          tma_load_2d_hint(w_ring + (size_t)ws.stage * kABytes, &tmap_w, QK == Q_INT4 ? kb * 8 : kb * 64,
-                           pc.n_tile * kBlockW, &ctl->w_full[ws.stage], kEvictFirst);
-        }
-        __syncwarp();
-        TL_STAMP(TL_PROD, lin);
-        ws.advance();
-      }
-    }
+    while (w_lin < nrb) w_issue(true);
   } else if (warp == kWarpXProd) {
     // ===================== activation producer =====================
     pdl_wait_prior();                        // the activations are the previous kernel's output
@@ -502,8 +578,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     for (int pi = 0; pi < wr.npieces; ++pi) {
       const Piece pc = wr.piece(pi);
       for (int rb = pc.rb_lo; rb < pc.rb_hi; ++rb) {
-        qwait(&ctl->x_empty[xs.stage], xs.phase ^ 1, p.debug);
-        if (p.debug & DBG_NO_XLOAD) {
+        qwait(&ctl->x_empty[xs.stage], xs.phase ^ 1, debug);
+        if (debug & DBG_NO_XLOAD) {
           if (elect_one()) mbar_arrive(&ctl->x_full[xs.stage]);
         } else if (elect_one()) {
           mbar_arrive_expect_tx(&ctl->x_full[xs.stage], kXStage);
@@ -535,7 +611,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int rb = mma_idx; rb < nrb; rb += mma_warps) {
         const int gsub0 = rb * RW;                                       // first operand sub-block of this raw block
         TL_STAMP(7, rb);
-        qwait(&ctl->x_full[rstage], rphase, p.debug);                         // activation sub-tiles (TMA)
+        qwait(&ctl->x_full[rstage], rphase, debug);                         // activation sub-tiles (TMA)
         tc_fence_after();
         TL_STAMP(TL_MMA_READY, rb);
         int steps_here = steps_total - rb * (RW * 4);
@@ -550,9 +626,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (mma_warps == 2 && steps_here == RW * 4) {
           // aligned mode: 1 or 2 whole segments per raw block
           if (seg_steps == RW * 4)
-            issue_raw_block<QK, BT, RW * 4>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, p.debug);
+            issue_raw_block<QK, BT, OPS, RW * 4>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, debug, p.subwait);
           else
-            issue_raw_block<QK, BT, RW * 2>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, p.debug);
+            issue_raw_block<QK, BT, OPS, RW * 2>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, debug, p.subwait);
         } else if (elect_one()) {
 #pragma unroll
           for (int st = 0; st < RW * 4; ++st) {
@@ -560,12 +636,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               const int buf = seg % NB;
               const int ostage = (gsub0 + (st >> 2)) % kOpStages;
               if ((st & 3) == 0) {
-                qwait(&ctl->op_full[ostage], ((gsub0 + (st >> 2)) / kOpStages) & 1, p.debug);   // dequantised sub-block
+                qwait(&ctl->op_full[ostage], ((gsub0 + (st >> 2)) / kOpStages) & 1, debug);   // dequantised sub-block
                 tc_fence_after();
               }
               if (!seg_open) {
                 // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
-                qwait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1, p.debug);
+                qwait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1, debug);
                 tc_fence_after();
               }
               const uint64_t bdesc = bdesc0 + (uint64_t)(((st >> 2) * kXBytes) >> 4) + 2 * (st & 3);
@@ -601,32 +677,13 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
     for (int j = 0; j < BT; ++j) acc[j] = 0.f;
 
-    // this row's scales / zero points were requested at kernel entry (see above); wait for them here
-    int tab_cols = 0;                                      // table columns in use (scale groups over all pieces)
-    for (int pi = 0; pi < wr.npieces; ++pi) {
-      const Piece pc = wr.piece(pi);
-      if (p.sk_ctas > 0) tab_cols += (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
-      else tab_cols += (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len + 1;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");   // every thread reads back only its own row
-    if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 2] = clock64();
-
     // int4: an integer zero point is subtracted exactly by the dequant warps (same HFMA2 that removes the fp16
     // magic offset), which leaves a scale-only epilogue.  A zero point that is not an integer in [0, 1023]
     // cannot be folded exactly: then the whole CTA falls back to  acc += s * (P - z * xsum)  with xsum = the
-    // segment's activation row sums (computed here from global memory; rare, correctness path only).
-    bool need_xsum = false;
-    if (QK == Q_INT4) {
-      bool bad = p.force_xsum || (p.debug & DBG_FORCE_XSUM);
-      for (int g = 0; g < tab_cols; ++g) {                 // rows past N hold zeros
-        const float z = zero_tab[epi_tid * tab_pitch + g];
-        bad |= !(z >= 0.f && z <= 1023.f && z == rintf(z));
-      }
-      if (bad) atomicOr(&ctl->need_xsum, 1);
-      asm volatile("bar.sync 4, 384;" ::: "memory");        // with the 8 dequant warps: tables + flag are visible
-      need_xsum = ctl->need_xsum != 0;
-      if (need_xsum) pdl_wait_prior();   // the fallback reads the activations (the previous kernel's output) from global
-    }
+    // segment's activation row sums (computed here from global memory; rare, correctness path only).  The
+    // decision was taken by the table-fill threads and ORed across the CTA by the set-up barrier.
+    const bool need_xsum = QK == Q_INT4 && cta_need_xsum;
+    if (need_xsum) pdl_wait_prior();   // the fallback reads the activations (the previous kernel's output) from global
     if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 3] = clock64();
     constexpr int PARTS = 128 / BT;
     const int xs_m = epi_tid / PARTS, xs_part = epi_tid % PARTS;
@@ -673,13 +730,13 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           asm volatile("bar.sync 3, 128;" ::: "memory");
         }
         const int buf = seg % NB;
-        const float sc = lds_f32(scale_tab + epi_tid * tab_pitch + tcol);        // rows past N hold zeros
+        const float sc = lds_f32(scale_tab + tcol * kTabPitch + epi_tid);        // rows past N hold zeros
         float zp = 0.f;
-        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + epi_tid * tab_pitch + tcol);
-        qwait(&ctl->acc_full[buf], (seg / NB) & 1, p.debug);
+        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + tcol * kTabPitch + epi_tid);
+        qwait(&ctl->acc_full[buf], (seg / NB) & 1, debug);
         tc_fence_after();
         if (warp == kWarpEpi0) TL_STAMP(TL_EPI_START, seg);
-        if ((p.debug & DBG_SKIP_DRAIN) && k_next < k_lim) {
+        if ((debug & DBG_SKIP_DRAIN) && k_next < k_lim) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
@@ -789,10 +846,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int sub_first = p.sk_ctas > 0 ? 0 : k_begin / 64;
     const int g_first = p.sk_ctas > 0 ? 0 : k_begin / seg_len;
     const int g_last = (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len;
-    if (QK == Q_INT4) {
-      asm volatile("bar.sync 4, 384;" ::: "memory");        // zero-point table (written by the epilogue threads) + flag
-      fold_zero = ctl->need_xsum == 0;
-    }
+    if (QK == Q_INT4) fold_zero = !cta_need_xsum;
     if (tl && warp == 0 && lane == 0) tl[kTlMisc + 4] = clock64();
     // ring position of this group's next raw block, advanced by 2 per iteration (ring depths are even, so no
     // integer division -- it cost ~30 ALU-pipe instructions per raw block on the pipe that bounds this kernel)
@@ -809,12 +863,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           if (fold_zero) {
             int g = ((sub_first + rb * 4 + sub) >> p.seg_shift) - g_first;
             g = g < g_last ? g : g_last;                     // blocks past K are multiplied by zero activations
-            z = lds_f32(zero_tab + row * tab_pitch + g);
+            z = lds_f32(zero_tab + g * kTabPitch + row);
           }
           adds[sub] = __floats2half2_rn(-1024.f - z, -64.f - z);
         }
       }
-      qwait(&ctl->w_full[rstage], rphase, p.debug);
+      qwait(&ctl->w_full[rstage], rphase, debug);
       const uint8_t* rawrow = w_ring + (size_t)rstage * kABytes + row * 128;
       uint4 raw[8];                                          // the row's 128 raw bytes (8 swizzled 16-byte chunks)
 #pragma unroll
@@ -831,16 +885,16 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int gsub = rb * RW + sub;
         if (gsub < nsub_total) {                               // sub-blocks past the k-range have no MMA step
           const int ostage = gsub % kOpStages;
-          qwait(&ctl->op_empty[ostage], ((gsub / kOpStages) & 1) ^ 1, p.debug);
+          qwait(&ctl->op_empty[ostage], ((gsub / kOpStages) & 1) ^ 1, debug);
           tc_fence_after();
           uint32_t vals[32];
           if (QK == Q_INT4) {
             const uint4 w0 = raw[sub * 2], w1 = raw[sub * 2 + 1];
             const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            if (p.debug & DBG_RAW_OPERAND) {
+            if (debug & DBG_RAW_OPERAND) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { vals[4 * j] = ws[j]; vals[4 * j + 1] = ws[j] ^ 1u; vals[4 * j + 2] = ws[j] ^ 2u; vals[4 * j + 3] = ws[j] ^ 3u; }
-            } else if (p.debug & DBG_PAIR_K4) {
+            } else if (debug & DBG_PAIR_K4) {
               const __half2 mul = __halves2half2(__float2half(1.0f), __float2half(1.0f));
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -877,7 +931,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
           }
-          if (!(p.debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 32, vals);
+          if (!(debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 32, vals);
           else asm volatile("" ::"r"(vals[0] ^ vals[7] ^ vals[13] ^ vals[31]));
           pending = ostage;
         }
@@ -897,10 +951,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (tl && threadIdx.x == 0) tl[kTlMisc + 6] = clock64();
-  if (p.timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
+  if (timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.timeline[kTlCta + 3 * blockIdx.x + 1] = (long long)gt;
+    timeline[kTlCta + 3 * blockIdx.x + 1] = (long long)gt;
   }
   if (warp == kWarpMma0) tmem_dealloc(tmem_base, kTmemCols);
 }
@@ -929,7 +983,7 @@ static inline void quant_rings(int qk, SplitPlan& pl, int blocks, int max_groups
   // activation blocks (L2-resident, held until their MMAs retire) get the smaller share, the raw weight ring
   // (HBM latency x bandwidth) everything that is left
   const int x_stage = rw * pl.bt * kStageKBytes;
-  const int fixed = 1024 + 1024 + 1024 /*xsum exchange*/ + max_groups * kBlockW * 4 * (qk == Q_INT4 ? 2 : 1);
+  const int fixed = 1024 + 1024 + 1024 /*xsum exchange*/ + ((max_groups * kTabPitch + 3) & ~3) * 4 * (qk == Q_INT4 ? 2 : 1);
   const int budget = b2l_max_smem_optin() - fixed;
   int xs = 4, wsn;
   while (xs > 2 && budget - xs * x_stage < 3 * kABytes) --xs;
@@ -1012,10 +1066,17 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
   return pl;
 }
 
-template <int QK, int BT>
-static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
-                       cudaStream_t st) {
-  auto kern = gemm_quant_kernel<QK, BT>;
+static int g_opstages = -1;         // env B2L_OPSTAGES=8 keeps the 8-deep operand ring (A/B measurements)
+static int g_subwait = -1;          // env B2L_SUBWAIT=0: MMA warps wait for whole segments
+static inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? atoi(e) : dflt;
+}
+
+template <int QK, int BT, int OPS, bool DBG>
+static int launch_q_inst(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
+                         cudaStream_t st) {
+  auto kern = gemm_quant_kernel<QK, BT, OPS, DBG>;
   static int configured_smem = 0;
   if (pl.smem_bytes > configured_smem) {
     B2L_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
@@ -1026,6 +1087,21 @@ static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const Quant
   b2l_launch(kern, dim3(grid), dim3(kQuantThreads), (size_t)(pl.smem_bytes), st, tw, tx, p);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
+}
+
+// Operand ring depth: 12 sub-stages (three raw blocks of int4) when they fit next to the four accumulator buffers
+// (token tile <= 32), else 8.  With 8 a dequant group could not start raw block i+2 before the MMAs of block i had
+// retired, which serialised conversion and tensor-pipe latency (device timeline, profiles/).
+template <int QK, int BT>
+static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
+                       cudaStream_t st) {
+  if (g_opstages < 0) g_opstages = env_int("B2L_OPSTAGES", 12);
+  const bool dbg = p.debug != 0 || p.timeline != nullptr;
+  if constexpr (4 * BT + 12 * 32 <= 512) {
+    if (g_opstages >= 12)
+      return dbg ? launch_q_inst<QK, BT, 12, true>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, 12, false>(tw, tx, p, pl, st);
+  }
+  return dbg ? launch_q_inst<QK, BT, 8, true>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, 8, false>(tw, tx, p, pl, st);
 }
 
 template <int QK>
@@ -1050,6 +1126,8 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   if ((g_debug & DBG_HALF_RING) && p.w_stages >= 4) p.w_stages = (p.w_stages / 2) & ~1;
   p.timeline = g_timeline;
   p.debug = g_debug;
+  if (g_subwait < 0) g_subwait = env_int("B2L_SUBWAIT", 1);
+  p.subwait = g_subwait;
   p.x = x; p.ldx = x_row_stride;
   p.force_xsum = 0; p.seg_shift = 0;
   if (qk == Q_INT4) {
@@ -1100,8 +1178,12 @@ extern "C" int b2l_debug_set_timeline(void* device_buffer) {
   gemm::g_timeline = (long long*)device_buffer;
   return B2L_OK;
 }
+// bits 0..15: DBG_* experiments (run the DBG instantiation); bit 16: 8-deep operand ring; bit 17: per-segment MMA
+// waits -- the last two select product code paths for A/B timing and do not switch to the DBG instantiation
 extern "C" int b2l_debug_set_flags(int flags) {
-  gemm::g_debug = flags;
+  gemm::g_debug = flags & 0xFFFF;
+  gemm::g_opstages = (flags & (1 << 16)) ? 8 : gemm::env_int("B2L_OPSTAGES", 12);
+  gemm::g_subwait = (flags & (1 << 17)) ? 0 : gemm::env_int("B2L_SUBWAIT", 1);
   return B2L_OK;
 }
 

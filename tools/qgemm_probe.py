@@ -18,7 +18,7 @@ import lite_llama_b200.kernels as K  # noqa: E402
 from lite_llama_b200 import _lib  # noqa: E402
 
 SHAPES = {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 4096), "down": (4096, 14336)}
-FLAGS = {"noX": 4096, "halfring": 8192, "skipall": 144+768, "skipall+noX": 144+768+4096, "skipall+halfring": 144+768+8192, "spin": 1024, "short": 2048, "A+few_mma+no_sttm+spin": 144+768+1024, "A+few_mma+no_sttm+short": 144+768+2048, "no_streamk+spin": 64+1024, "no_streamk+short": 64+2048, "A": 144, "A+few_mma": 144 + 256, "A+no_sttm": 144 + 512, "A+few_mma+no_sttm": 144 + 768, "few_mma": 256, "no_sttm": 512, "skip_drain": 128, "skip_drain+raw": 144, "skip_drain+pair_k4": 160, "base": 0, "raw_operand": 16, "pair_k4": 32, "no_streamk": 64, "no_streamk+pair_k4": 96, "no_streamk+raw": 80}
+FLAGS = {"ops8": 65536, "segwait": 131072, "ops8+segwait": 196608, "dbg_inst": 32768, "noX": 4096, "halfring": 8192, "skipall": 144+768, "skipall+noX": 144+768+4096, "skipall+halfring": 144+768+8192, "spin": 1024, "short": 2048, "A+few_mma+no_sttm+spin": 144+768+1024, "A+few_mma+no_sttm+short": 144+768+2048, "no_streamk+spin": 64+1024, "no_streamk+short": 64+2048, "A": 144, "A+few_mma": 144 + 256, "A+no_sttm": 144 + 512, "A+few_mma+no_sttm": 144 + 768, "few_mma": 256, "no_sttm": 512, "skip_drain": 128, "skip_drain+raw": 144, "skip_drain+pair_k4": 160, "base": 0, "raw_operand": 16, "pair_k4": 32, "no_streamk": 64, "no_streamk+pair_k4": 96, "no_streamk+raw": 80}
 
 
 def main():

@@ -85,10 +85,11 @@ def main():
     names = ["PROD", "MMA_READY", "MMA_ISSUED", "DQ_START", "DQ_DONE", "EPI_START", "EPI_DONE"]
     t0 = int(t[t > 0].min())
     print(f"== {a.op} m={a.m} n={a.n} k={a.k}: total cycles {int(t[t>0].max()) - t0}")
-    misc = tl.cpu()[3072:3072 + 8]
+    misc = tl.cpu()[3072:3072 + 11]
     m0 = int(misc[0])
     names_misc = ["kernel entry", "setup sync done", "epi: tables landed", "epi: zero check + bar4 done",
-                  "dequant: past bar4", "epi: last segment drained", "exit sync"]
+                  "dequant: past bar4", "epi: last segment drained", "exit sync", "epi: table cp.async issued",
+                  "producer: mbarriers initialised", "mma0: TMEM allocated", "warp 0: reached setup sync"]
     print("start-up / shutdown stamps (cycles from kernel entry; first TL stamp at %d):" % (t0 - m0))
     for nm, v in zip(names_misc, misc.tolist()):
         print(f"  {nm:28s} {int(v) - m0 if v > 0 else -1}")
