@@ -133,6 +133,23 @@ int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, const void* sc
                      int64_t y_row_stride, void* workspace, int64_t workspace_bytes, void* counters,
                      int64_t num_counters, void* stream);
 
+/* Load-time repack of the three W4A16 tensors into the kernel-native layout (the reference reserves this seam:
+ * lite_llama/models/quantization/_layout/__init__.py:1-6; its own tensors stay as w4a16.py:9-12 defines them).
+ * Bit-exact permutations, one pass each:
+ *   qweight_packed int32 [N, K/8]: nibble position p of a word holds the K index [0,2,4,6,1,3,5,7][p] of that word
+ *   table_packed   fp32 [ceil(N/128)][groups][128]: table_packed[t][g][r] = table[128 t + r][g], rows past N zero
+ * b2l_w4a16_matmul_packed computes exactly b2l_w4a16_matmul's result from the repacked tensors; zeros_foldable = 1
+ * promises that every zero point is an integer in [0, 1023] (checked once by the packer's caller). */
+int b2l_w4a16_pack_qweight(void* out, const void* in, int64_t n, int64_t k8, int64_t in_row_stride,
+                           int64_t out_row_stride, void* stream);
+int b2l_w4a16_pack_table(void* out, const void* in, int64_t n, int64_t groups, int64_t row_stride,
+                         int64_t col_stride, void* stream);
+int b2l_w4a16_matmul_packed(void* y, const void* x, const void* qweight_packed, const void* scales_packed,
+                            const void* zeros_packed, const void* bias, int bias_is_f32, int64_t m, int64_t n,
+                            int64_t k, int group_size, int zeros_foldable, int64_t x_row_stride,
+                            int64_t qw_row_stride, int64_t y_row_stride, void* workspace, int64_t workspace_bytes,
+                            void* counters, int64_t num_counters, void* stream);
+
 /* w8a16_matmul(x, qweight, scales, *, group_n, group_k, bias)
  * -- lite_llama/kernels/quantization/w8a16.py:155-216.  qweight uint8 (fp8-e4m3 bits) or int8. */
 int b2l_w8a16_matmul(void* y, const void* x, const void* qweight, int weight_is_fp8, const void* scales,

@@ -41,8 +41,10 @@ constexpr int kQuantThreads = 16 * 32;      // 2 x 4 dequant warps, 4 epilogue, 
 // slot behind the dequant warps of their sub-partition.  warp % 4 = TMEM lane quadrant for dequant / epilogue.
 constexpr int kWarpEpi0 = 8;                // epilogue warps 8..11
 constexpr int kWarpXProd = 12, kWarpWProd = 13, kWarpMma1 = 14, kWarpMma0 = 15;
-constexpr int kMaxOpStages = 12;            // TMEM operand sub-stages (64 K elements = 32 columns each): template parameter OPS
+constexpr int kMaxOpStages = 6;             // TMEM operand stages (two 64-element sub-blocks = 64 columns each)
 constexpr int kMaxRawStages = 8;
+// operand ring depth: 6 stages (three raw blocks of int4) when they fit next to the four accumulator buffers
+__host__ __device__ constexpr int op_stages_for(int bt) { return 4 * bt + 6 * 64 <= 512 ? 6 : 4; }
 constexpr int kTabPitch = 129;            // floats per scale-table column (128 weight rows + 1: conflict-free both ways)
 
 enum QuantKind { Q_INT4 = 0, Q_FP8 = 1, Q_INT8 = 2 };
@@ -69,7 +71,7 @@ struct QuantParams {
   int w_stages, x_stages;                  // ring depths: raw weight blocks / activation blocks
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
   int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
-  int subwait;                             // MMA warps wait per 64-element sub-block (1) or per whole segment (0)
+  int zeros_foldable;                      // packed layout: the packer verified that every zero point is an integer in [0, 1023]
   long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
   int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
@@ -88,6 +90,7 @@ __device__ __forceinline__ void qwait(uint64_t* bar, uint32_t parity, int debug)
   else mbar_wait(bar, parity);
 }
 constexpr int kTlCta = 4096;    // timeline: [1024][3] per-CTA {globaltimer at entry, at exit, SM id}
+constexpr int kTlSub = 3072 + 32;   // timeline: [96][5] per-sub-block stamps of dequant warp 0
 constexpr int kTlMisc = 3072;   // timeline: start-up / shutdown stamps of CTA (0,0,0), see tools/timeline.py
 
 // role rows of the debug timeline
@@ -109,6 +112,7 @@ struct __align__(8) QControl {
   uint64_t op_empty[kMaxOpStages];
   uint64_t acc_full[4];
   uint64_t acc_empty[4];
+  uint64_t tab_full;                       // packed layout: the scale / zero-point tables have landed (bulk copies)
   uint32_t tmem_base;
   int is_last;
 };
@@ -250,92 +254,67 @@ __device__ __forceinline__ void st_release_smem(int* p, int v) {
 }
 
 // Hand-off granularity.  Weights arrive per RAW BLOCK (one 128-byte-wide TMA tile: 256 int4 / 128 8-bit K
-// values); the dequantised operand is handed to the MMA warps per 64-element SUB-BLOCK (32 TMEM columns, 4 MMA
-// steps) through a ring of kOpStages = 8 sub-stages.  With whole-block operand stages only 3 fitted next to
-// the accumulators, each stayed occupied for dequant + MMA latency (~3000 cycles), and that -- not bandwidth,
-// not the ALU pipe -- set the pace at ~1100 cycles per raw block (device timeline, profiles/).
-// 8 sub-stages = two raw blocks of int4, so a sub-stage is always written by the same dequant warp group
-// (groups alternate raw blocks) and every waiter follows every phase of the barriers it waits on.
-//
-// Fast issue path of one full raw block whose K range holds NSEG whole segments of SEG_STEPS MMA steps each
-// (scale group divides the raw block).  Everything but the stage addresses is a compile-time constant, so the
-// elected lane runs a straight line of UTCHMMA/UTCBAR; a device timeline showed that ~40 bookkeeping
-// instructions per step in the generic loop cost 160 cycles per MMA against 16 cycles of tensor-pipe time.
-template <int QK, int BT, int OPS, int SEG_STEPS>
-__device__ __forceinline__ void issue_raw_block(QControl* ctl, uint32_t tmem_base, uint32_t a_base, uint64_t bdesc0,
-                                                int seg0, int gsub0, uint64_t* x_empty, long long* tl, int debug, int subwait) {
-  constexpr int kOpStages = OPS;
+// values); the dequantised operand is handed to the MMA warps per OPERAND STAGE of two 64-element sub-blocks
+// (64 TMEM columns, 8 MMA steps) through a ring of 6 stages (4 when the token tile is 64).  History (device
+// timelines under profiles/): whole-block stages -- only 3 fitted -- stayed occupied for dequant + MMA latency;
+// single sub-block stages paid one barrier wait, two tcgen05 fences, one tcgen05.wait::st and one arrive per
+// KiB of weights and warp, ~400 of the ~800 cycles a sub-block took.
+
+// MMA issue of one full raw block whose K range holds whole segments of SPS sub-blocks each (scale group divides the
+// raw block): one operand stage (two sub-blocks, 8 MMA steps) per elected-lane block, every offset a compile-time
+// constant.  The issuing warp shares its scheduler with two dequant warps and gets an issue slot every ~4-6
+// cycles, so its instruction count -- not the tensor pipe (16 cycles per MMA at 32 tokens: tools/mma_rate.cu) --
+// sets the pace of the accumulator hand-offs: ~25 instructions per sub-block here against ~90 in a rolled loop
+// with run-time stage arithmetic (700 cycles per segment on the device timeline, profiles/).
+template <int QK, int BT, int NST, int SPS>
+__device__ __forceinline__ void issue_block(QControl* ctl, uint32_t tmem_base, uint32_t a_base, uint64_t bdesc0,
+                                            int seg0, int gst0, uint64_t* x_empty, int debug) {
   constexpr int RW = raw_sub<QK>();
-  constexpr int NSEG = RW * 4 / SEG_STEPS;
-  constexpr int SPS = SEG_STEPS / 4;              // operand sub-blocks per segment
   constexpr int NB = 4;
   constexpr int kXBytes = BT * kStageKBytes;
   constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
 #pragma unroll
-  for (int s = 0; s < NSEG; ++s) {
-    const int seg = seg0 + s;
-    const int buf = seg & (NB - 1);
-    const uint32_t d = tmem_base + buf * BT;
-    // accumulator buffer `buf` must have been drained (segment seg-NB) by all four epilogue warps
-    qwait(&ctl->acc_empty[buf], ((seg / NB) & 1) ^ 1, debug);
-    if (subwait) {
-      // issue each 64-element sub-block as soon as ITS operand stage is full: the dequant warps run one sub-block
-      // ahead of the tensor pipe instead of a whole segment ahead
-#pragma unroll
-      for (int q = 0; q < SPS; ++q) {
-        const int gsub = gsub0 + s * SPS + q;
-        const int ostage = gsub % kOpStages;
-        qwait(&ctl->op_full[ostage], (gsub / kOpStages) & 1, debug);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int st = (s * SPS + q) * 4 + j;
-            if (!(debug & DBG_FEW_MMA) || j == 3)
-              umma_f16_ts(d, a_base + ostage * 32 + j * 8,
-                          bdesc0 + (uint64_t)((((st >> 2) * kXBytes) >> 4) + 2 * j), idesc, (q > 0 || j > 0) ? 1u : 0u);
-          }
-          tc_commit(&ctl->op_empty[ostage]);
-          if (q == SPS - 1) {
-            tc_commit(&ctl->acc_full[buf]);
-            if (s == NSEG - 1) tc_commit(x_empty);
-          }
-        }
-        __syncwarp();
-      }
-      continue;
-    }
-#pragma unroll
-    for (int q = 0; q < SPS; ++q) {
-      const int gsub = gsub0 + s * SPS + q;
-      qwait(&ctl->op_full[gsub % kOpStages], (gsub / kOpStages) & 1, debug);
-    }
+  for (int sp = 0; sp < RW / 2; ++sp) {
+    const int gst = gst0 + sp;
+    const int ostage = gst % NST;
+    // segments touched by this stage: sub-blocks 2sp and 2sp+1
+    const int segA = seg0 + (2 * sp) / SPS, segB = seg0 + (2 * sp + 1) / SPS;
+    if ((2 * sp) % SPS == 0) qwait(&ctl->acc_empty[segA & (NB - 1)], ((segA / NB) & 1) ^ 1, debug);
+    if (SPS == 1) qwait(&ctl->acc_empty[segB & (NB - 1)], ((segB / NB) & 1) ^ 1, debug);
+    qwait(&ctl->op_full[ostage], (gst / NST) & 1, debug);
     tc_fence_after();
-    if (tl && seg < 128 && (threadIdx.x & 31) == 0) tl[2048 + seg * 2] = clock64();
     if (elect_one()) {
+      const uint32_t a_addr = a_base + ostage * 64;
 #pragma unroll
-      for (int j = 0; j < SEG_STEPS; ++j) {
-        const int st = s * SEG_STEPS + j;
-        const int ostage = (gsub0 + (st >> 2)) % kOpStages;
-        if (!(debug & DBG_FEW_MMA) || (st & 3) == 3)
-          umma_f16_ts(d, a_base + ostage * 32 + (st & 3) * 8,
-                      bdesc0 + (uint64_t)((((st >> 2) * kXBytes) >> 4) + 2 * (st & 3)), idesc, j > 0 ? 1u : 0u);
-        if ((st & 3) == 3) tc_commit(&ctl->op_empty[ostage]);
+      for (int h = 0; h < 2; ++h) {
+        const int sub = 2 * sp + h;
+        const int sseg = h ? segB : segA;
+        const uint32_t d = tmem_base + (sseg & (NB - 1)) * BT;
+        const uint64_t bd = bdesc0 + (uint64_t)((sub * kXBytes) >> 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (!(debug & DBG_FEW_MMA) || j == 3)
+            umma_f16_ts(d, a_addr + h * 32 + j * 8, bd + 2 * j, idesc, (sub % SPS != 0 || j > 0) ? 1u : 0u);
+        if (sub % SPS == SPS - 1) tc_commit(&ctl->acc_full[sseg & (NB - 1)]);
       }
-      tc_commit(&ctl->acc_full[buf]);
-      if (s == NSEG - 1) tc_commit(x_empty);
+      tc_commit(&ctl->op_empty[ostage]);
+      if (sp == RW / 2 - 1) tc_commit(x_empty);
     }
     __syncwarp();
-    if (tl && seg < 128 && (threadIdx.x & 31) == 0) tl[2048 + seg * 2 + 1] = clock64();
   }
 }
 
-template <int QK, int BT, int OPS, bool DBG>
+// LAYOUT (int4 only): 0 = the reference's tensors as they are; 1 = the load-time repack of b2l_w4a16_pack_* (nibbles
+// of a word interleaved so that one LOP3 extracts a K-consecutive pair, scale / zero tables tiled [tile][group][128
+// rows] so that a CTA's share is one contiguous bulk copy per piece).
+template <int QK, int BT, bool DBG, int LAYOUT>
 __global__ void __launch_bounds__(kQuantThreads, 1)
 gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const QuantParams p) {
   using T = __half;
+  constexpr int OPS = op_stages_for(BT);
   constexpr int kOpStages = OPS;
+  constexpr int TP = LAYOUT == 1 ? kBlockW : kTabPitch;   // floats per table column
   // the debug experiments and the timeline stamps only exist in the DBG instantiation (selected by the host when a
   // debug flag or a timeline buffer is set): the product kernel carries none of their code
   const int debug = DBG ? p.debug : 0;
@@ -361,10 +340,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int tab_floats = (p.max_groups * kTabPitch + 3) & ~3;
   float* zero_tab = scale_tab + tab_floats;
   float* xs_smem = zero_tab + (QK == Q_INT4 ? tab_floats : 0);   // [2][BT] per-segment xsum exchange
-  // TMEM map (columns): [NB accumulator buffers of BT] [kOpStages operand sub-stages of 32]
+  // TMEM map (columns): [NB accumulator buffers of BT] [kOpStages operand stages of 64]
   constexpr int NB = 4;
   constexpr int kAColBase = NB * BT;
-  constexpr int kColsUsed = kAColBase + kOpStages * 32;
+  constexpr int kColsUsed = kAColBase + kOpStages * 64;
   constexpr int kTmemCols = kColsUsed <= 32 ? 32 : kColsUsed <= 64 ? 64 : kColsUsed <= 128 ? 128
                           : kColsUsed <= 256 ? 256 : 512;
   static_assert(kColsUsed <= 512, "TMEM budget exceeded");
@@ -438,9 +417,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   };
 
   // int4: this thread saw a zero point that cannot be folded (or the group size rules folding out altogether)
-  int bad_zero = (QK == Q_INT4 && (p.force_xsum || (debug & DBG_FORCE_XSUM))) ? 1 : 0;
+  int bad_zero = (QK == Q_INT4 && (p.force_xsum || (debug & DBG_FORCE_XSUM) || (LAYOUT == 1 && !p.zeros_foldable))) ? 1 : 0;
   constexpr int kFillWarps = kWarpEpi0 + 4;
-  if (warp < kFillWarps) {
+  if (LAYOUT == 0 && warp < kFillWarps) {
     // ---- warps 0..11 (idle until the first weights land): stage the scale / zero-point table ----
     // A lane owns table columns `lane` and `lane + 32` (a CTA keeps at most 64 scale groups: host), warp w copies
     // rows w, w+12, ...: global reads are coalesced along a weight row's groups and the transposed shared-memory
@@ -543,15 +522,44 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_init(&ctl->acc_full[s], 1);
         mbar_init(&ctl->acc_empty[s], 4);
       }
+      if (LAYOUT == 1) mbar_init(&ctl->tab_full, 1);
       mbar_fence_init();
       fence_proxy_async_smem();
+      if (LAYOUT == 1) {
+        // packed tables: a piece's groups x 128 rows are contiguous in global memory -> one bulk copy per table
+        // and piece, requested before the weight stream so that they are not queued behind it
+        const int G = p.K / seg_len;
+        int total_cols = 0;
+        for (int pi = 0; pi < wr.npieces; ++pi) {
+          const Piece pc = wr.piece(pi);
+          if (p.sk_ctas > 0) total_cols += (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
+          else total_cols += (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len + 1;
+        }
+        mbar_arrive_expect_tx(&ctl->tab_full, (uint32_t)total_cols * kBlockW * 4 * 2);
+        int tcol = 0;
+        for (int pi = 0; pi < wr.npieces; ++pi) {
+          const Piece pc = wr.piece(pi);
+          int g_first, g_count;
+          if (p.sk_ctas > 0) {
+            g_first = pc.rb_lo * kRawK / seg_len;
+            g_count = (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
+          } else {
+            g_first = k_begin / seg_len;
+            g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+          }
+          const size_t src = ((size_t)pc.n_tile * G + g_first) * kBlockW;
+          bulk_g2s(zero_tab + tcol * kBlockW, p.zeros + src, (uint32_t)g_count * kBlockW * 4, &ctl->tab_full);
+          bulk_g2s(scale_tab + tcol * kBlockW, p.scales + src, (uint32_t)g_count * kBlockW * 4, &ctl->tab_full);
+          tcol += g_count;
+        }
+      }
       if (tl) tl[kTlMisc + 8] = clock64();
     }
     __syncwarp();
     // Weights are static: under programmatic dependent launch this stream starts while the previous kernel is
     // still running (no griddepcontrol.wait on this path) -- and before the rest of the CTA has finished setting up,
     // but after the table requests are on their way (see above).
-    asm volatile("bar.sync 5, %0;" ::"n"((kFillWarps + 1) * 32) : "memory");
+    if (LAYOUT == 0) asm volatile("bar.sync 5, %0;" ::"n"((kFillWarps + 1) * 32) : "memory");
     const int pre = nrb < p.w_stages ? nrb : p.w_stages;
     for (int i = 0; i < pre; ++i) w_issue(false);
   }
@@ -624,19 +632,21 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
         const uint64_t bdesc0 = x_desc0 + (uint64_t)((rstage * kXStage) >> 4);
         if (mma_warps == 2 && steps_here == RW * 4) {
-          // aligned mode: 1 or 2 whole segments per raw block
+          // aligned mode: the raw block holds 1 or 2 whole segments
+          const int gst0 = gsub0 >> 1;
           if (seg_steps == RW * 4)
-            issue_raw_block<QK, BT, OPS, RW * 4>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, debug, p.subwait);
+            issue_block<QK, BT, OPS, RW>(ctl, tmem_base, a_base, bdesc0, seg, gst0, &ctl->x_empty[rstage], debug);
           else
-            issue_raw_block<QK, BT, OPS, RW * 2>(ctl, tmem_base, a_base, bdesc0, seg, gsub0, &ctl->x_empty[rstage], tl, debug, p.subwait);
+            issue_block<QK, BT, OPS, RW / 2>(ctl, tmem_base, a_base, bdesc0, seg, gst0, &ctl->x_empty[rstage], debug);
         } else if (elect_one()) {
 #pragma unroll
           for (int st = 0; st < RW * 4; ++st) {
             if (st < steps_here) {
               const int buf = seg % NB;
-              const int ostage = (gsub0 + (st >> 2)) % kOpStages;
-              if ((st & 3) == 0) {
-                qwait(&ctl->op_full[ostage], ((gsub0 + (st >> 2)) / kOpStages) & 1, debug);   // dequantised sub-block
+              const int gst = (gsub0 + (st >> 2)) >> 1;          // operand stage = two sub-blocks (gsub0 is even)
+              const int ostage = gst % kOpStages;
+              if ((st & 7) == 0) {
+                qwait(&ctl->op_full[ostage], (gst / kOpStages) & 1, debug);   // dequantised stage
                 tc_fence_after();
               }
               if (!seg_open) {
@@ -645,8 +655,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 tc_fence_after();
               }
               const uint64_t bdesc = bdesc0 + (uint64_t)(((st >> 2) * kXBytes) >> 4) + 2 * (st & 3);
-              umma_f16_ts(tmem_base + buf * BT, a_base + ostage * 32 + (st & 3) * 8, bdesc, idesc, seg_open ? 1u : 0u);
-              if ((st & 3) == 3 || st == steps_here - 1) tc_commit(&ctl->op_empty[ostage]);
+              umma_f16_ts(tmem_base + buf * BT, a_base + ostage * 64 + (st & 7) * 8, bdesc, idesc, seg_open ? 1u : 0u);
+              if ((st & 7) == 7 || st == steps_here - 1) tc_commit(&ctl->op_empty[ostage]);
               --seg_left;
               if (seg_left == 0) {
                 tc_commit(&ctl->acc_full[buf]);
@@ -683,6 +693,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // segment's activation row sums (computed here from global memory; rare, correctness path only).  The
     // decision was taken by the table-fill threads and ORed across the CTA by the set-up barrier.
     const bool need_xsum = QK == Q_INT4 && cta_need_xsum;
+    if (LAYOUT == 1) mbar_wait(&ctl->tab_full, 0);
     if (need_xsum) pdl_wait_prior();   // the fallback reads the activations (the previous kernel's output) from global
     if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 3] = clock64();
     constexpr int PARTS = 128 / BT;
@@ -730,9 +741,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           asm volatile("bar.sync 3, 128;" ::: "memory");
         }
         const int buf = seg % NB;
-        const float sc = lds_f32(scale_tab + tcol * kTabPitch + epi_tid);        // rows past N hold zeros
+        const float sc = lds_f32(scale_tab + tcol * TP + epi_tid);        // rows past N hold zeros
         float zp = 0.f;
-        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + tcol * kTabPitch + epi_tid);
+        if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + tcol * TP + epi_tid);
         qwait(&ctl->acc_full[buf], (seg / NB) & 1, debug);
         tc_fence_after();
         if (warp == kWarpEpi0) TL_STAMP(TL_EPI_START, seg);
@@ -847,25 +858,34 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int g_first = p.sk_ctas > 0 ? 0 : k_begin / seg_len;
     const int g_last = (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len;
     if (QK == Q_INT4) fold_zero = !cta_need_xsum;
+    if (LAYOUT == 1) mbar_wait(&ctl->tab_full, 0);
     if (tl && warp == 0 && lane == 0) tl[kTlMisc + 4] = clock64();
     // ring position of this group's next raw block, advanced by 2 per iteration (ring depths are even, so no
     // integer division -- it cost ~30 ALU-pipe instructions per raw block on the pipe that bounds this kernel)
     int rstage = half;
     uint32_t rphase = 0;
     for (int rb = half; rb < nrb; rb += 2) {
-      // zero points of this block's four 64-element sub-blocks (each lies in one scale group); fetched before
-      // the barrier waits so that the table latency is off the conversion's critical path
-      __half2 adds[4];
+      // zero points of this block's 64-element sub-blocks (each lies in one scale group), fetched before the barrier
+      // waits so that the table latency is off the conversion's critical path.  Reference layout: one add
+      // {-(1024+z), -(64+z)} per (low nibble, high nibble) pair; packed layout: add_lo = {-(1024+z)} x2 for the
+      // low-nibble pairs, add_hi = {-(64+z)} x2 for the high-nibble pairs.
+      __half2 add_lo[RW], add_hi[RW];
       if (QK == Q_INT4) {
 #pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
+        for (int sub = 0; sub < RW; ++sub) {
           float z = 0.f;
           if (fold_zero) {
-            int g = ((sub_first + rb * 4 + sub) >> p.seg_shift) - g_first;
+            int g = ((sub_first + rb * RW + sub) >> p.seg_shift) - g_first;
             g = g < g_last ? g : g_last;                     // blocks past K are multiplied by zero activations
-            z = lds_f32(zero_tab + g * kTabPitch + row);
+            z = lds_f32(zero_tab + g * TP + row);
           }
-          adds[sub] = __floats2half2_rn(-1024.f - z, -64.f - z);
+          if (LAYOUT == 1) {
+            add_lo[sub] = __float2half2_rn(-1024.f - z);
+            add_hi[sub] = __float2half2_rn(-64.f - z);
+          } else {
+            add_lo[sub] = __floats2half2_rn(-1024.f - z, -64.f - z);
+            add_hi[sub] = add_lo[sub];
+          }
         }
       }
       qwait(&ctl->w_full[rstage], rphase, debug);
@@ -883,19 +903,31 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
       for (int sub = 0; sub < RW; ++sub) {
         const int gsub = rb * RW + sub;
+        constexpr int CPS = 8 / RW;                            // 16-byte chunks of the row per sub-block
+        // DBG: five clock stamps per sub-block of warp 0 (loop top, operand stage free, converted, previous store
+        // retired + announced, store issued): tools/timeline.py prints the phase lengths
+        long long* const tls = (DBG && tl && warp == 0 && lane == 0 && gsub < 96) ? tl + kTlSub + gsub * 5 : nullptr;
+        if (tls) tls[0] = clock64();
         if (gsub < nsub_total) {                               // sub-blocks past the k-range have no MMA step
-          const int ostage = gsub % kOpStages;
-          qwait(&ctl->op_empty[ostage], ((gsub / kOpStages) & 1) ^ 1, debug);
-          tc_fence_after();
+          const int gst = gsub >> 1;                           // operand stage = sub-blocks (2i, 2i+1); rb * RW is even
+          const int ostage = gst % kOpStages;
+          if ((sub & 1) == 0) {
+            qwait(&ctl->op_empty[ostage], ((gst / kOpStages) & 1) ^ 1, debug);
+            tc_fence_after();
+          }
+          if (tls) tls[1] = clock64();
           uint32_t vals[32];
           if (QK == Q_INT4) {
-            const uint4 w0 = raw[sub * 2], w1 = raw[sub * 2 + 1];
+            const uint4 w0 = raw[sub * CPS], w1 = raw[sub * CPS + CPS - 1];
             const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             if (debug & DBG_RAW_OPERAND) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { vals[4 * j] = ws[j]; vals[4 * j + 1] = ws[j] ^ 1u; vals[4 * j + 2] = ws[j] ^ 2u; vals[4 * j + 3] = ws[j] ^ 3u; }
-            } else if (debug & DBG_PAIR_K4) {
-              const __half2 mul = __halves2half2(__float2half(1.0f), __float2half(1.0f));
+            } else if (LAYOUT == 1) {
+              // packed word: nibble positions hold K indices [0,2,4,6,1,3,5,7] -> each LOP3 yields a K-consecutive
+              // pair; low-nibble pairs are 1024 + n, high-nibble pairs 1024 + 16 n (5 ALU-pipe instructions per
+              // word instead of 8)
+              const __half2 one = __float2half2_rn(1.0f), sixteenth = __float2half2_rn(0.0625f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const uint32_t w8 = ws[j] >> 8;
@@ -903,10 +935,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 const uint32_t h1 = lop3_and_or(ws[j], 0x00F000F0u, 0x64006400u);
                 const uint32_t h2 = lop3_and_or(w8, 0x000F000Fu, 0x64006400u);
                 const uint32_t h3 = lop3_and_or(w8, 0x00F000F0u, 0x64006400u);
-                const __half2 v0 = __hfma2(*reinterpret_cast<const __half2*>(&h0), mul, adds[sub]);
-                const __half2 v1 = __hfma2(*reinterpret_cast<const __half2*>(&h1), mul, adds[sub]);
-                const __half2 v2 = __hfma2(*reinterpret_cast<const __half2*>(&h2), mul, adds[sub]);
-                const __half2 v3 = __hfma2(*reinterpret_cast<const __half2*>(&h3), mul, adds[sub]);
+                const __half2 v0 = __hfma2(*reinterpret_cast<const __half2*>(&h0), one, add_lo[sub]);
+                const __half2 v1 = __hfma2(*reinterpret_cast<const __half2*>(&h1), sixteenth, add_hi[sub]);
+                const __half2 v2 = __hfma2(*reinterpret_cast<const __half2*>(&h2), one, add_lo[sub]);
+                const __half2 v3 = __hfma2(*reinterpret_cast<const __half2*>(&h3), sixteenth, add_hi[sub]);
                 vals[4 * j] = *reinterpret_cast<const uint32_t*>(&v0);
                 vals[4 * j + 1] = *reinterpret_cast<const uint32_t*>(&v1);
                 vals[4 * j + 2] = *reinterpret_cast<const uint32_t*>(&v2);
@@ -914,26 +946,36 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], adds[sub], vals + 4 * j);
+              for (int j = 0; j < 8; ++j) dequant_int4_word(ws[j], add_lo[sub], vals + 4 * j);
             }
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const uint4 w = raw[sub * 4 + c];
+              const uint4 w = raw[(sub * CPS + c) % 8];
               const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) dequant_w8_word(ws[j], QK == Q_FP8, vals + 8 * c + 2 * j);
             }
           }
-          if (pending >= 0) {
+          if (tls) {
+            long long t;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(vals[0]), "r"(vals[15]), "r"(vals[31]) : "memory");
+            tls[2] = t;
+          }
+          // the previous stage is announced after the conversion of this stage's first half: by then its
+          // tcgen05.st have retired and tcgen05.wait::st does not wait
+          if ((sub & 1) == 0 && pending >= 0) {
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
+            pending = -1;
           }
-          if (!(debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 32, vals);
+          if (tls) tls[3] = clock64();
+          if (!(debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 64 + (sub & 1) * 32, vals);
           else asm volatile("" ::"r"(vals[0] ^ vals[7] ^ vals[13] ^ vals[31]));
-          pending = ostage;
+          if (tls) tls[4] = clock64();
+          if ((sub & 1) == 1 || gsub == nsub_total - 1) pending = ostage;
         }
       }
       if (pending >= 0) {
@@ -1066,17 +1108,15 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
   return pl;
 }
 
-static int g_opstages = -1;         // env B2L_OPSTAGES=8 keeps the 8-deep operand ring (A/B measurements)
-static int g_subwait = -1;          // env B2L_SUBWAIT=0: MMA warps wait for whole segments
 static inline int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e && e[0] ? atoi(e) : dflt;
 }
 
-template <int QK, int BT, int OPS, bool DBG>
+template <int QK, int BT, bool DBG, int LAYOUT>
 static int launch_q_inst(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
                          cudaStream_t st) {
-  auto kern = gemm_quant_kernel<QK, BT, OPS, DBG>;
+  auto kern = gemm_quant_kernel<QK, BT, DBG, LAYOUT>;
   static int configured_smem = 0;
   if (pl.smem_bytes > configured_smem) {
     B2L_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
@@ -1089,28 +1129,24 @@ static int launch_q_inst(const CUtensorMap& tw, const CUtensorMap& tx, const Qua
   return B2L_OK;
 }
 
-// Operand ring depth: 12 sub-stages (three raw blocks of int4) when they fit next to the four accumulator buffers
-// (token tile <= 32), else 8.  With 8 a dequant group could not start raw block i+2 before the MMAs of block i had
-// retired, which serialised conversion and tensor-pipe latency (device timeline, profiles/).
 template <int QK, int BT>
 static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
-                       cudaStream_t st) {
-  if (g_opstages < 0) g_opstages = env_int("B2L_OPSTAGES", 12);
+                       cudaStream_t st, int layout) {
   const bool dbg = p.debug != 0 || p.timeline != nullptr;
-  if constexpr (4 * BT + 12 * 32 <= 512) {
-    if (g_opstages >= 12)
-      return dbg ? launch_q_inst<QK, BT, 12, true>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, 12, false>(tw, tx, p, pl, st);
+  if constexpr (QK == Q_INT4) {
+    if (layout == 1)
+      return dbg ? launch_q_inst<QK, BT, true, 1>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, false, 1>(tw, tx, p, pl, st);
   }
-  return dbg ? launch_q_inst<QK, BT, 8, true>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, 8, false>(tw, tx, p, pl, st);
+  return dbg ? launch_q_inst<QK, BT, true, 0>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, false, 0>(tw, tx, p, pl, st);
 }
 
 template <int QK>
 static int launch_q(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
-                    cudaStream_t st) {
+                    cudaStream_t st, int layout = 0) {
   switch (pl.bt) {
-    case 16: return launch_q_bt<QK, 16>(tw, tx, p, pl, st);
-    case 32: return launch_q_bt<QK, 32>(tw, tx, p, pl, st);
-    default: return launch_q_bt<QK, 64>(tw, tx, p, pl, st);
+    case 16: return launch_q_bt<QK, 16>(tw, tx, p, pl, st, layout);
+    case 32: return launch_q_bt<QK, 32>(tw, tx, p, pl, st, layout);
+    default: return launch_q_bt<QK, 64>(tw, tx, p, pl, st, layout);
   }
 }
 
@@ -1126,8 +1162,7 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   if ((g_debug & DBG_HALF_RING) && p.w_stages >= 4) p.w_stages = (p.w_stages / 2) & ~1;
   p.timeline = g_timeline;
   p.debug = g_debug;
-  if (g_subwait < 0) g_subwait = env_int("B2L_SUBWAIT", 1);
-  p.subwait = g_subwait;
+  p.zeros_foldable = 0;
   p.x = x; p.ldx = x_row_stride;
   p.force_xsum = 0; p.seg_shift = 0;
   if (qk == Q_INT4) {
@@ -1178,12 +1213,9 @@ extern "C" int b2l_debug_set_timeline(void* device_buffer) {
   gemm::g_timeline = (long long*)device_buffer;
   return B2L_OK;
 }
-// bits 0..15: DBG_* experiments (run the DBG instantiation); bit 16: 8-deep operand ring; bit 17: per-segment MMA
-// waits -- the last two select product code paths for A/B timing and do not switch to the DBG instantiation
+// DBG_* experiments: any non-zero flag runs the DBG instantiation of the kernel
 extern "C" int b2l_debug_set_flags(int flags) {
   gemm::g_debug = flags & 0xFFFF;
-  gemm::g_opstages = (flags & (1 << 16)) ? 8 : gemm::env_int("B2L_OPSTAGES", 12);
-  gemm::g_subwait = (flags & (1 << 17)) ? 0 : gemm::env_int("B2L_SUBWAIT", 1);
   return B2L_OK;
 }
 
@@ -1231,6 +1263,90 @@ extern "C" int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, con
   p.scales = (const float*)scales; p.zeros = (const float*)zeros; p.s_stride_n = s_row_stride; p.s_stride_k = s_col_stride;
   p.group_n = 1; p.group_k = group_size;
   return launch_q<Q_INT4>(tw, tx, p, pl, (cudaStream_t)stream);
+}
+
+// Same product on the load-time repack of the three tensors (b2l_w4a16_pack_qweight / b2l_w4a16_pack_table):
+// qweight_packed int32 [N, K/8] with the nibbles of each word in K order [0,2,4,6,1,3,5,7]; scales_packed /
+// zeros_packed fp32 [ceil(N/128)][K/group][128] (rows past N zero).  zeros_foldable = 1 when the caller has checked
+// that every zero point is an integer in [0, 1023] (else the row-sum correction path runs).
+extern "C" int b2l_w4a16_matmul_packed(void* y, const void* x, const void* qweight_packed, const void* scales_packed,
+                                       const void* zeros_packed, const void* bias, int bias_is_f32, int64_t m,
+                                       int64_t n, int64_t k, int group_size, int zeros_foldable, int64_t x_row_stride,
+                                       int64_t qw_row_stride, int64_t y_row_stride, void* workspace,
+                                       int64_t workspace_bytes, void* counters, int64_t num_counters, void* stream) {
+  B2L_REQUIRE(y && x && qweight_packed && scales_packed && zeros_packed, "w4a16_matmul_packed: null pointer");
+  B2L_REQUIRE(m >= 0 && n > 0 && k > 0 && k % 8 == 0, "w4a16_matmul_packed: bad shape m=%lld n=%lld k=%lld",
+              (long long)m, (long long)n, (long long)k);
+  B2L_REQUIRE(group_size > 0 && k % group_size == 0,
+              "w4a16_matmul_packed: K (%lld) must be a multiple of group_size (%d)", (long long)k, group_size);
+  B2L_REQUIRE(group_size % 16 == 0, "w4a16_matmul_packed: group_size (%d) must be a multiple of 16", group_size);
+  B2L_REQUIRE(x_row_stride % 8 == 0 && qw_row_stride % 4 == 0,
+              "w4a16_matmul_packed: row strides must be 16-byte multiples (K a multiple of 32)");
+  B2L_REQUIRE((uintptr_t)scales_packed % 16 == 0 && (uintptr_t)zeros_packed % 16 == 0,
+              "w4a16_matmul_packed: tables must be 16-byte aligned");
+  if (m == 0) return B2L_OK;
+  QuantParams p; SplitPlan pl; CUtensorMap tw, tx;
+  int rc = quant_common(Q_INT4, p, pl, y, x, qweight_packed, m, n, k, x_row_stride, qw_row_stride, y_row_stride,
+                        workspace, workspace_bytes, counters, num_counters, &tw, &tx, "w4a16_matmul_packed", group_size);
+  if (rc != B2L_OK) return rc;
+  p.bias = bias; p.bias_is_f32 = bias_is_f32;
+  p.scales = (const float*)scales_packed; p.zeros = (const float*)zeros_packed; p.s_stride_n = 0; p.s_stride_k = 0;
+  p.group_n = 1; p.group_k = group_size;
+  p.zeros_foldable = zeros_foldable ? 1 : 0;
+  return launch_q<Q_INT4>(tw, tx, p, pl, (cudaStream_t)stream, 1);
+}
+
+// ---- load-time repack kernels of the packed W4A16 layout (one pass each, bit-exact permutations) ----
+namespace {
+__global__ void w4_pack_qweight_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int64_t n, int64_t k8,
+                                       int64_t in_stride, int64_t out_stride) {
+  pdl_prologue();
+  const int64_t total = n * k8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k8, c = i % k8;
+    const uint32_t w = in[r * in_stride + c];
+    // position p of the packed word holds K index order[p], order = [0,2,4,6,1,3,5,7]
+    uint32_t o = 0;
+#pragma unroll
+    for (int pidx = 0; pidx < 8; ++pidx) {
+      const int kk = pidx < 4 ? 2 * pidx : 2 * (pidx - 4) + 1;
+      o |= ((w >> (4 * kk)) & 0xFu) << (4 * pidx);
+    }
+    out[r * out_stride + c] = o;
+  }
+}
+__global__ void w4_pack_table_kernel(float* __restrict__ out, const float* __restrict__ in, int64_t n, int64_t g,
+                                     int64_t stride_n, int64_t stride_k, int64_t tiles) {
+  pdl_prologue();
+  const int64_t total = tiles * g * 128;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i % 128, gi = (i / 128) % g, t = i / (128 * g);
+    const int64_t row = t * 128 + r;
+    out[i] = row < n ? in[row * stride_n + gi * stride_k] : 0.f;
+  }
+}
+}  // namespace
+
+extern "C" int b2l_w4a16_pack_qweight(void* out, const void* in, int64_t n, int64_t k8, int64_t in_row_stride,
+                                      int64_t out_row_stride, void* stream) {
+  B2L_REQUIRE(out && in && n > 0 && k8 > 0, "w4a16_pack_qweight: bad arguments");
+  const int64_t total = n * k8;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  b2l_launch(w4_pack_qweight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (uint32_t*)out,
+             (const uint32_t*)in, n, k8, in_row_stride, out_row_stride);
+  B2L_LAUNCH_CHECK();
+  return B2L_OK;
+}
+extern "C" int b2l_w4a16_pack_table(void* out, const void* in, int64_t n, int64_t groups, int64_t row_stride,
+                                    int64_t col_stride, void* stream) {
+  B2L_REQUIRE(out && in && n > 0 && groups > 0, "w4a16_pack_table: bad arguments");
+  const int64_t tiles = (n + 127) / 128;
+  const int64_t total = tiles * groups * 128;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  b2l_launch(w4_pack_table_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (float*)out, (const float*)in, n,
+             groups, row_stride, col_stride, tiles);
+  B2L_LAUNCH_CHECK();
+  return B2L_OK;
 }
 
 extern "C" int b2l_w8a16_matmul(void* y, const void* x, const void* qweight, int weight_is_fp8, const void* scales,

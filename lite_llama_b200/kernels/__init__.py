@@ -14,7 +14,7 @@ from .skip_rmsnorm import skip_rmsnorm
 from .swiglu import swiglu_forward
 from .update_kv_buffer import update_kv_buffer, update_kv_buffer_split
 from .update_kv_index import update_kv_index
-from .quantization import smoothquant_matmul, w4a16_matmul, w8a16_matmul
+from .quantization import PackedW4, smoothquant_matmul, w4a16_matmul, w4a16_matmul_packed, w4a16_pack, w8a16_matmul
 
 __all__ = [
     "flash_attention2_no_pad",
@@ -33,4 +33,7 @@ __all__ = [
     "w4a16_matmul",
     "w8a16_matmul",
     "smoothquant_matmul",
+    "w4a16_pack",
+    "w4a16_matmul_packed",
+    "PackedW4",
 ]

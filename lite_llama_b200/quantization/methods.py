@@ -7,11 +7,12 @@ Mirrors the reference's strategy registry (lite_llama/models/quantization/method
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
 
-from ..kernels import linear, smoothquant_matmul, w4a16_matmul, w8a16_matmul
+from ..kernels import PackedW4, linear, smoothquant_matmul, w4a16_matmul, w4a16_matmul_packed, w4a16_pack, w8a16_matmul
 from .params import quantize_fp8_per_channel, quantize_int4_groupwise, quantize_int8_per_channel
 
 LINEAR_METHODS = ("fp16", "int4", "int8", "fp8", "smoothquant")
@@ -30,12 +31,15 @@ class LinearWeights:
     zeros: torch.Tensor | None = None
     bias: torch.Tensor | None = None
     group_size: int = 128
+    packed: PackedW4 | None = None          # int4: kernel-native repack (replaces qweight/scales/zeros)
 
     def nbytes(self) -> int:
         total = 0
         for t in (self.weight, self.qweight, self.scales, self.zeros, self.bias):
             if t is not None:
                 total += t.numel() * t.element_size()
+        if self.packed is not None:
+            total += self.packed.nbytes()
         return total
 
 
@@ -48,6 +52,11 @@ def make_linear_weights(weight: torch.Tensor, method: str, bias: torch.Tensor | 
         return LinearWeights(method, n, k, weight=weight.contiguous(), bias=bias)
     if method == "int4":
         q, s, z = quantize_int4_groupwise(weight, group_size)
+        if q.is_cuda and os.environ.get("B2L_W4_LAYOUT", "packed") != "reference":
+            # load-time repack into the kernel-native layout (the reference's `_layout` seam); the reference-layout
+            # tensors are not kept, so a projection is stored exactly once
+            return LinearWeights(method, n, k, bias=bias, group_size=group_size,
+                                 packed=w4a16_pack(q, s, z, group_size=group_size))
         return LinearWeights(method, n, k, qweight=q, scales=s, zeros=z, bias=bias, group_size=group_size)
     if method in ("int8", "smoothquant"):
         q, s = quantize_int8_per_channel(weight)
@@ -63,6 +72,8 @@ def apply_linear(x: torch.Tensor, w: LinearWeights) -> torch.Tensor:
     if w.method == "fp16":
         return linear(x, w.weight, w.bias)
     if w.method == "int4":
+        if w.packed is not None:
+            return w4a16_matmul_packed(x, w.packed, bias=w.bias)
         return w4a16_matmul(x, w.qweight, w.scales, w.zeros, group_size=w.group_size, bias=w.bias)
     if w.method in ("int8", "fp8"):
         return w8a16_matmul(x, w.qweight, w.scales, group_n=1, group_k=w.in_features, bias=w.bias)

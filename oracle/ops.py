@@ -166,6 +166,41 @@ def w4a16_matmul(x, qweight, scales, zeros, group_size=128, bias=None):
     return out.to(x.dtype)
 
 
+W4_PACK_ORDER = (0, 2, 4, 6, 1, 3, 5, 7)   # K index (within a word) held by nibble position p of the packed word
+
+
+def pack_w4_qweight(qweight):
+    """Kernel-native nibble order of ``include/b200_lite_kernels.h: b2l_w4a16_pack_qweight``: a pure permutation
+    of the reference word (kernels/quantization/w4a16.py:9-12: nibble j = K index 8i+j) -- position p of the
+    packed word holds the reference nibble ``W4_PACK_ORDER[p]``."""
+    word = qweight.to(torch.int64) & 0xFFFFFFFF
+    out = torch.zeros_like(word)
+    for pos, kk in enumerate(W4_PACK_ORDER):
+        out |= ((word >> (4 * kk)) & 0xF) << (4 * pos)
+    out = torch.where(out >= 2**31, out - 2**32, out)
+    return out.to(torch.int32)
+
+
+def unpack_w4_packed(qweight_packed):
+    """Inverse view of :func:`pack_w4_qweight`: ``[N, K]`` nibbles in K order from the packed words."""
+    word = qweight_packed.to(torch.int64) & 0xFFFFFFFF
+    n = word.shape[0]
+    nib = torch.zeros(n, word.shape[1], 8, dtype=torch.int64)
+    for pos, kk in enumerate(W4_PACK_ORDER):
+        nib[:, :, kk] = (word >> (4 * pos)) & 0xF
+    return nib.reshape(n, -1)
+
+
+def pack_w4_table(table):
+    """``[N, G]`` fp32 scales or zero points -> ``[ceil(N/128), G, 128]`` (b2l_w4a16_pack_table): tile-major,
+    weight row fastest, rows past N zero."""
+    n, g = table.shape
+    tiles = (n + 127) // 128
+    padded = torch.zeros(tiles * 128, g, dtype=torch.float32)
+    padded[:n] = table.float()
+    return padded.view(tiles, 128, g).permute(0, 2, 1).contiguous()
+
+
 def quantize_int8_per_channel(weight):
     """models/quantization/params/int8.py:12-28."""
     scale = weight.abs().amax(dim=-1, keepdim=True).float() / 127.0

@@ -461,6 +461,74 @@ def test_w4a16_unpack_order_is_bit_exact():
     assert torch.equal(out.cpu().T.to(torch.int64), ops.unpack_int4(qw))
 
 
+# ---- kernel-native (load-time repacked) W4A16 layout: same product, bit for bit ----
+def _w4_packed(qw, sc, zp, gs):
+    return K().w4a16_pack(qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs)
+
+
+def test_w4a16_pack_matches_oracle():
+    n, k, gs = 300, 1152, 128
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), dtype=torch.int64).to(torch.int32)
+    sc = torch.rand(n, k // gs) + 0.5
+    zp = torch.randint(0, 16, (n, k // gs)).float()
+    pk = _w4_packed(qw, sc, zp, gs)
+    assert torch.equal(pk.qweight.cpu(), ops.pack_w4_qweight(qw))
+    assert torch.equal(pk.scales.cpu(), ops.pack_w4_table(sc))
+    assert torch.equal(pk.zeros.cpu(), ops.pack_w4_table(zp))
+    assert pk.zeros_foldable
+    zp[7, 2] = 3.5
+    assert not _w4_packed(qw, sc, zp, gs).zeros_foldable
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 256, 512), (8, 512, 1024), (32, 4096, 4096), (33, 130, 384), (100, 256, 2048),
+                                   (32, 512, 14336), (16, 640, 1792), (3, 130, 768), (32, 1000, 2304), (7, 128, 5120)])
+@pytest.mark.parametrize("gs", [32, 128])
+def test_w4a16_packed_matches_oracle_and_reference_layout(m, n, k, gs):
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    w = torch.randn(n, k, dtype=torch.float32) * 0.05
+    qw, sc, zp = ops.quantize_int4_groupwise(w, gs)
+    bias = torch.randn(n)
+    out = K().w4a16_matmul_packed(x, _w4_packed(qw, sc, zp, gs), bias=bias.cuda())
+    close(out, ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs, bias), **GEMM_TOL)
+    # same exact integer operand values, same accumulation order: identical to the reference-layout kernel
+    assert torch.equal(out, K().w4a16_matmul(x, qw.cuda(), sc.cuda(), zp.cuda(), group_size=gs, bias=bias.cuda()))
+
+
+def test_w4a16_packed_fractional_zero_points():
+    m, n, k, gs = 9, 384, 2048, 256
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), dtype=torch.int64).to(torch.int32)
+    sc = torch.rand(n, k // gs) * 0.01 + 0.001
+    zp = torch.rand(n, k // gs) * 15
+    pk = _w4_packed(qw, sc, zp, gs)
+    assert not pk.zeros_foldable
+    close(K().w4a16_matmul_packed(x, pk), ops.w4a16_matmul(x.cpu(), qw, sc, zp, gs), **GEMM_TOL)
+
+
+def test_w4a16_packed_unpack_order_is_bit_exact():
+    n, k, gs = 128, 256, 128
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), dtype=torch.int64).to(torch.int32)
+    x = torch.eye(k, dtype=torch.float16, device="cuda")
+    pk = _w4_packed(qw, torch.ones(n, k // gs), torch.zeros(n, k // gs), gs)
+    out = K().w4a16_matmul_packed(x, pk)
+    assert torch.equal(out.cpu().T.to(torch.int64), ops.unpack_int4(qw))
+
+
+@pytest.mark.parametrize("n,k", [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)])
+@pytest.mark.parametrize("m", [1, 32])
+def test_w4a16_packed_llama3_8b_projection_shapes(m, n, k):
+    gs = 128
+    torch.manual_seed(1)
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5
+    qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), device="cuda", dtype=torch.int64).to(torch.int32)
+    sc = torch.rand(n, k // gs, device="cuda") * 0.004 + 0.001
+    zp = torch.randint(0, 16, (n, k // gs), device="cuda").float()
+    out = K().w4a16_matmul_packed(x, K().w4a16_pack(qw, sc, zp, group_size=gs))
+    assert torch.equal(out, K().w4a16_matmul(x, qw, sc, zp, group_size=gs))
+    for _ in range(2):
+        assert torch.equal(out, K().w4a16_matmul_packed(x, K().w4a16_pack(qw, sc, zp, group_size=gs)))
+
+
 def test_w8a16_golden():
     for c in load_golden("w8a16")["cases"]:
         x = c["x"].cuda()

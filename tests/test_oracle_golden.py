@@ -145,3 +145,21 @@ def test_known_answers_norm(residual):
     y, res = ops.skip_rmsnorm(x, r, w, 1e-6)
     torch.testing.assert_close(y.float(), w.float().expand(2, 64), rtol=1e-3, atol=1e-3)
     assert torch.equal(res, torch.full((2, 64), 5.0, dtype=torch.float16) if residual else x)
+
+
+def test_w4_pack_is_a_permutation_of_the_reference_layout():
+    # the kernel-native repack must carry exactly the reference's nibbles (w4a16.py:9-12) and table entries
+    torch.manual_seed(0)
+    qw = torch.randint(-(2**31), 2**31 - 1, (130, 24), dtype=torch.int64).to(torch.int32)
+    packed = ops.pack_w4_qweight(qw)
+    assert packed.dtype == torch.int32 and packed.shape == qw.shape
+    assert torch.equal(ops.unpack_w4_packed(packed), ops.unpack_int4(qw))
+    # known answer: nibbles 0..7 in K order -> positions hold K indices [0,2,4,6,1,3,5,7]
+    one = torch.tensor([[0x76543210]], dtype=torch.int32)
+    assert int(ops.pack_w4_qweight(one)[0, 0]) == 0x75316420
+    tab = torch.randn(130, 6)
+    pt = ops.pack_w4_table(tab)
+    assert pt.shape == (2, 6, 128)
+    for n in (0, 1, 127, 128, 129):
+        assert torch.equal(pt[n // 128, :, n % 128], tab[n])
+    assert float(pt[1, :, 2:].abs().max()) == 0.0

@@ -45,12 +45,18 @@ def main():
             ws.append((qw, sc, zp))
         nbytes = n * k // 2 + n * (k // 128) * 8
         row = {"shape": name, "m": a.m, "n": n, "k": k}
+        packed = [K.w4a16_pack(qw, sc, zp, group_size=128) for qw, sc, zp in ws]
         for fname in a.flags.split(","):
-            lib.b2l_debug_set_flags(FLAGS[fname])
+            use_packed = fname.startswith("packed")
+            lib.b2l_debug_set_flags(FLAGS[fname[7:] if fname.startswith("packed+") else ("base" if use_packed else fname)])
 
             def fn():
-                for qw, sc, zp in ws:
-                    K.w4a16_matmul(x, qw, sc, zp, group_size=128)
+                if use_packed:
+                    for pk in packed:
+                        K.w4a16_matmul_packed(x, pk)
+                else:
+                    for qw, sc, zp in ws:
+                        K.w4a16_matmul(x, qw, sc, zp, group_size=128)
 
             fn()
             torch.cuda.synchronize()

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--hot", type=int, default=0, help="launches issued right before the stamped one (sustained-load clocks)")
     ap.add_argument("--brief", action="store_true")
+    ap.add_argument("--packed", action="store_true", help="kernel-native W4A16 layout (w4a16_pack)")
     a = ap.parse_args()
     lib = _lib.load()
     lib.b2l_debug_set_timeline.argtypes = [ctypes.c_void_p]
@@ -41,9 +42,14 @@ def main():
             sets.append((qw, sc, zp))
         calls = [0]
 
+        packed = [K.w4a16_pack(*t, group_size=128) for t in sets] if a.packed else None
+
         def fn():
-            qw, sc, zp = sets[calls[0] % len(sets)]
+            i = calls[0] % len(sets)
             calls[0] += 1
+            if packed is not None:
+                return K.w4a16_matmul_packed(x, packed[i])
+            qw, sc, zp = sets[i]
             return K.w4a16_matmul(x, qw, sc, zp, group_size=128)
     else:
         qw = torch.randint(0, 120, (a.n, a.k), device=dev, dtype=torch.uint8)
@@ -112,6 +118,15 @@ def main():
         a0, a1 = int(flat[2 * sg]), int(flat[2 * sg + 1])
         if a0 > 0:
             print(f"  seg {sg}: {a0 - t0} -> {a1 - t0}  ({a1 - a0})")
+    sub = tl.cpu()[3072 + 32:3072 + 32 + 96 * 5].view(96, 5)
+    if int((sub > 0).sum()) > 0:
+        print("dequant warp 0, per 64-element sub-block (cycles): top->stage free | convert | wait::st+arrive | st issue | gap to next top")
+        for i in range(96):
+            if int(sub[i, 0]) <= 0:
+                continue
+            nxt = [int(sub[j, 0]) for j in range(i + 1, 96) if int(sub[j, 0]) > 0]
+            gap = (nxt[0] - int(sub[i, 4])) if nxt else -1
+            print(f"  gsub {i:3d} @{int(sub[i,0]) - t0:7d}: {int(sub[i,1]-sub[i,0]):5d} | {int(sub[i,2]-sub[i,1]):5d} | {int(sub[i,3]-sub[i,2]):5d} | {int(sub[i,4]-sub[i,3]):5d} | {gap:5d}")
     nrb = int((t[0] > 0).sum())
     
 
