@@ -60,6 +60,9 @@ def workload_config(args, world):
         "prompt_len": args.prompt_len, "parallelism": f"dp{world}" if world > 1 else "single",
         "l2_policy": "inputs_larger_than_l2 (4.98 GB of weights streamed per step vs 126 MB L2)",
         "cuda_graph": "one captured graph per decode step",
+        "weight_layout": ("int4 tensors repacked once at load into the kernel-native layout (bit-exact nibble / table "
+                          "permutation, lite_llama_b200.kernels.w4a16_pack); B2L_W4_LAYOUT=reference keeps the "
+                          "reference's tensors") if args.quant == "int4" else "reference",
     }
 
 

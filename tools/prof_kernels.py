@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--k", type=int, default=4096)
     ap.add_argument("--ctx", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=4)
+    ap.add_argument("--reference-layout", action="store_true", help="w4a16: the reference's tensors instead of the load-time repack")
     a = ap.parse_args()
     dev = "cuda"
     if a.op in ("w4a16", "w8a16", "dense", "w8a8"):
@@ -29,7 +30,11 @@ def main():
             qw = torch.randint(-(2**31), 2**31 - 1, (a.n, a.k // 8), device=dev, dtype=torch.int64).to(torch.int32)
             sc = torch.rand(a.n, a.k // 128, device=dev) * 0.01
             zp = torch.full((a.n, a.k // 128), 8.0, device=dev)
-            fn = lambda: K.w4a16_matmul(x, qw, sc, zp, group_size=128)
+            if a.reference_layout:
+                fn = lambda: K.w4a16_matmul(x, qw, sc, zp, group_size=128)
+            else:
+                pk = K.w4a16_pack(qw, sc, zp, group_size=128)
+                fn = lambda: K.w4a16_matmul_packed(x, pk)
         elif a.op == "w8a16":
             qw = torch.randint(0, 120, (a.n, a.k), device=dev, dtype=torch.uint8)
             sc = torch.rand((a.n + 127) // 128, (a.k + 127) // 128, device=dev)
