@@ -115,9 +115,6 @@ struct __align__(8) QControl {
   uint64_t tab_full;                       // packed layout: the scale / zero-point tables have landed (bulk copies)
   uint32_t tmem_base;
   int is_last;
-  // tiles this CTA finished last (stream-K / split-K): reduced by all threads after the role loops
-  int nfix;
-  int fix_tile[4], fix_ntile[4], fix_sharers[4];
 };
 static_assert(sizeof(QControl) <= 1024, "control block too large");
 
@@ -526,7 +523,6 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_init(&ctl->acc_empty[s], 4);
       }
       if (LAYOUT == 1) mbar_init(&ctl->tab_full, 1);
-      ctl->nfix = 0;
       mbar_fence_init();
       fence_proxy_async_smem();
       if (LAYOUT == 1) {
@@ -831,14 +827,14 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
         for (int j = 0; j < BT; ++j) mine[j * kBlockW + epi_tid] = __float_as_uint(acc[j]);
         if (splitk_ticket(p.counters, tile_id, sharers, epi_tid, &ctl->is_last)) {
-          // last finisher of the tile: the partial sums are added up by ALL threads of the CTA once the role loops
-          // are over (see the end of the kernel) -- 128 epilogue threads walking the slots one after the other
-          // made the tail of the short GEMMs 5 us long (per-CTA wall clock, profiles/)
-          if (epi_tid == 0) {
-            const int f = ctl->nfix;
-            ctl->fix_tile[f] = tile_id; ctl->fix_ntile[f] = pc.n_tile; ctl->fix_sharers[f] = sharers;
-            ctl->nfix = f + 1;
+#pragma unroll
+          for (int j = 0; j < BT; ++j) acc[j] = 0.f;
+          for (int s = 0; s < sharers; ++s) {
+            const uint32_t* src = base + (size_t)s * (BT * kBlockW) + epi_tid;
+#pragma unroll
+            for (int j = 0; j < BT; ++j) acc[j] += __uint_as_float(__ldcg(src + j * kBlockW));
           }
+          store_final();
         }
       }
 #pragma unroll
@@ -996,49 +992,6 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  // ---- split tiles this CTA finished last: out = sum of the partial tiles in slot order (deterministic) + bias ----
-  {
-    const int nfix = ctl->nfix;
-    const int slots_per_tile = p.sk_ctas > 0 ? p.sk_slots : p.splits;
-    constexpr int JT = kQuantThreads / kBlockW;            // token rows covered per pass
-    constexpr int NJ = BT / JT;
-    const int n_local = threadIdx.x % kBlockW, j_first = threadIdx.x / kBlockW;
-    for (int f = 0; f < nfix; ++f) {
-      const int sharers = ctl->fix_sharers[f];
-      const uint32_t* base = p.ws + (size_t)ctl->fix_tile[f] * slots_per_tile * (BT * kBlockW) + n_local;
-      float sum[NJ];
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) sum[i] = 0.f;
-      for (int s0 = 0; s0 < sharers; s0 += 4) {
-        float v[4][NJ];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int i = 0; i < NJ; ++i)
-            v[u][i] = s0 + u < sharers
-                          ? __uint_as_float(__ldcg(base + (size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW))
-                          : 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (s0 + u < sharers) {
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) sum[i] += v[u][i];
-          }
-      }
-      const int n = ctl->fix_ntile[f] * kBlockW + n_local;
-      if (n < p.N) {
-        float bv = 0.f;
-        if (p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
-                                       : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
-        __half* yy = reinterpret_cast<__half*>(p.y);
-#pragma unroll
-        for (int i = 0; i < NJ; ++i) {
-          const int m = blockIdx.y * BT + j_first + i * JT;
-          if (m < p.M) yy[(int64_t)m * p.ldy + n] = __float2half_rn(sum[i] + bv);
-        }
-      }
-    }
-  }
   if (tl && threadIdx.x == 0) tl[kTlMisc + 6] = clock64();
   if (timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
     unsigned long long gt;
