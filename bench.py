@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-transformers-on-CPU row (configs[0])")
+    ap.add_argument("--watchdog-s", type=int, default=1500, help="give up (exit 3) after this many seconds; 0 = never")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--cpu-layers", type=int, default=2, help="decoder layers in the CPU sample")
     return ap.parse_args()
@@ -64,6 +66,16 @@ def workload_config(args, world):
                           "permutation, lite_llama_b200.kernels.w4a16_pack); B2L_W4_LAYOUT=reference keeps the "
                           "reference's tensors") if args.quant == "int4" else "reference",
     }
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json), or
+    None when no capture of that kernel at this shape is on file."""
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        return json.loads(f.read_text())[kernel]["bytes"]
+    except Exception:
+        return None
 
 
 def peaks():
@@ -270,8 +282,21 @@ def kernel_breakdown(runner, batch: int, ctx: int, hbm_peak: float) -> list[dict
 
 
 # --------------------------------------------------------------------------- #
+def arm_watchdog(seconds: int) -> None:
+    """A hung kernel must not hold the GPU box until the caller's limit kills it: after `seconds` print what is
+    known and leave."""
+    def fire():
+        print(json.dumps({"error": f"bench.py watchdog: no result after {seconds} s (device hang?)"}), flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main() -> None:
     args = parse_args()
+    if args.watchdog_s > 0:
+        arm_watchdog(args.watchdog_s)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -439,7 +464,7 @@ def main() -> None:
             top = max(kb, key=lambda r: r["us_per_step"])
             line["roofline"] = {
                 "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": top["frac_hbm"], "traffic": ncu_traffic(top["kernel"]), "peak_source": peak_src,
                 "share_of_step": top["us_per_step"] / (dev_ms / K * 1e3),
             }
         except Exception as ex:  # the headline number must survive a breakdown failure
@@ -453,6 +478,16 @@ def main() -> None:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)[:300]}
+    if not args.no_cpu_baseline and not args.no_hf_baseline and world == 1:
+        # BASELINE.json configs[0]: HF transformers on the host cores (Qwen2.5-0.5B, greedy, one prompt) -- a reported
+        # baseline row in the same run (tools/bench_hf_baseline.py), not what the GPU number is compared against
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import bench_hf_baseline
+
+            line["hf_cpu_baseline"] = bench_hf_baseline.measure()
+        except Exception as ex:
+            line["hf_cpu_baseline"] = {"error": repr(ex)[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
