@@ -472,7 +472,7 @@ def main() -> None:
     if "roofline" not in line:
         line["roofline"] = {"bound": "hbm", "achieved": line["step_roofline"]["achieved_gbs"], "peak": hbm_peak,
                             "unit": "GB/s", "frac": line["step_roofline"]["frac"], "traffic": None}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported baselines: rank 0 at N = 1 only
         try:
             base = cpu_decode_sample(args, steps=3, warmup=1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
