@@ -107,3 +107,50 @@ def test_tensor_parallel_all_reduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_stream_k_partition_arithmetic():
+    """The (tile, raw block) split of the quantised GEMM (csrc/gemm_quant.cu: WorkRange / sk_owner) restated in
+    integers: CTA ranges tile the space exactly, `sk_owner` inverts the range formula, pieces add up, and the
+    host's `workspace slots per tile` (b2l_quant_gemm_plan) is the largest number of CTAs sharing a tile."""
+    import ctypes
+    import random
+
+    from lite_llama_b200 import _lib
+
+    def owner(lin, ctas, total):
+        return ((lin + 1) * ctas - 1) // total
+
+    def check(n_tiles, nrb_tile, ctas):
+        total = n_tiles * nrb_tile
+        cover = [0] * total
+        for c in range(ctas):
+            g0, g1 = c * total // ctas, (c + 1) * total // ctas
+            assert g1 > g0
+            for lin in range(g0, g1):
+                cover[lin] += 1
+                assert owner(lin, ctas, total) == c
+            t0 = g0 // nrb_tile
+            npieces = (g1 - 1) // nrb_tile - t0 + 1
+            blocks = 0
+            for i in range(npieces):
+                base = (t0 + i) * nrb_tile
+                lo, hi = max(g0 - base, 0), min(g1 - base, nrb_tile)
+                assert 0 <= lo < hi <= nrb_tile
+                blocks += hi - lo
+            assert blocks == g1 - g0
+        assert all(v == 1 for v in cover)
+        return max(owner((t + 1) * nrb_tile - 1, ctas, total) - owner(t * nrb_tile, ctas, total) + 1
+                   for t in range(n_tiles))
+
+    lib = _lib.load()
+    for n, k in [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (640, 1792), (1000, 2304)]:
+        out = (ctypes.c_int * 10)()
+        _lib.check(lib.b2l_quant_gemm_plan(0, 32, n, k, 128, out, None))
+        sk_ctas, slots, nrb_tile, n_tiles = out[0], out[1], out[2], out[3]
+        assert sk_ctas > 0 and nrb_tile == k // 256 and n_tiles == (n + 127) // 128
+        assert check(n_tiles, nrb_tile, sk_ctas) == slots
+    rng = random.Random(0)
+    for _ in range(300):
+        nt, nrb = rng.randint(1, 300), rng.randint(1, 64)
+        check(nt, nrb, max(1, min(nt * nrb // 2, 148)))
