@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-transformers-on-CPU row (configs[0])")
-    ap.add_argument("--watchdog-s", type=int, default=1500, help="give up (exit 3) after this many seconds; 0 = never")
+    ap.add_argument("--watchdog-s", type=int, default=600, help="give up (exit 3) after this many seconds; 0 = never")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--cpu-layers", type=int, default=2, help="decoder layers in the CPU sample")
     return ap.parse_args()
