@@ -54,6 +54,13 @@ int64_t b2l_launch_count(void);
  * overlap it; see csrc/common.cuh).  Returns the previous setting.  Also: environment B2L_PDL=0 at load.
  * No reference counterpart: the reference launches every Triton kernel fully serialised. */
 int b2l_set_pdl(int enabled);
+/* Device-side hang watchdog (csrc/common.cuh): every barrier wait of the warp-specialised kernels traps after
+ * B2L_HANG_MS milliseconds (environment, default 4000, 0 = off) instead of parking for ever, after writing a
+ * host-pinned record.  out16 receives: [0] 0xB2D00DED when a record exists, [1] FNV-1a hash of the source file's
+ * basename, [2] line of the wait, [3..5] blockIdx, [6] threadIdx.x, [7] shared address of the barrier, [8] parity,
+ * [9] ms waited, [10..12] gridDim, [13] blockDim.x.  Readable after the CUDA context has died.  No reference
+ * counterpart (Triton kernels have no cross-warp pipelines to dead-lock). */
+int b2l_hang_report(int* out16);
 
 /* skip_rmsnorm(X, residual, weight, eps) -- lite_llama/kernels/skip_rmsnorm.py:192-234.
  * residual (nullable) is updated in place with x + residual (rounded to dtype); y gets

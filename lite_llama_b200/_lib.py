@@ -75,6 +75,30 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+def _fnv1a(name: str) -> int:
+    h = 2166136261
+    for c in name.encode():
+        h = ((h ^ c) * 16777619) & 0xFFFFFFFF
+    return h
+
+
+def hang_report() -> dict | None:
+    """Decode the device-side hang watchdog's record (csrc/common.cuh): which barrier wait of which kernel
+    source gave up. ``None`` when no kernel of the library has trapped. Works after the CUDA context died."""
+    lib = load()
+    buf = (ctypes.c_int * 16)()
+    lib.b2l_hang_report(buf)
+    w = [v & 0xFFFFFFFF for v in buf]
+    if w[0] != 0xB2D00DED:
+        return None
+    names = {_fnv1a(f.name): f.name for f in (_PKG / "csrc").glob("*.cu*")}
+    return {
+        "file": names.get(w[1], hex(w[1])), "line": w[2], "block": (w[3], w[4], w[5]), "thread": w[6],
+        "warp": w[6] // 32, "barrier_smem_addr": hex(w[7]), "parity": w[8], "waited_ms": w[9],
+        "grid": (w[10], w[11], w[12]), "block_dim": w[13],
+    }
+
+
 def last_error() -> str:
     return load().b2l_last_error().decode("utf-8", "replace")
 

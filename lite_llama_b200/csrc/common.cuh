@@ -168,10 +168,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
 // Pure polling (mbarrier.test_wait never suspends the thread): lowest wake-up latency, costs issue slots.
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -182,21 +178,94 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  while (!mbar_test_wait(bar, parity)) {
+// try_wait with the default (short, implementation-defined) suspend window instead of the long hint above
+__device__ __forceinline__ bool mbar_try_wait_short(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// ---- device-side hang watchdog -------------------------------------------- //
+// A pipeline bug in a warp-specialised kernel shows up as a warp parked on an mbarrier for ever: the GPU stays
+// "busy", the host blocks in the next synchronisation and nothing says which kernel, role or barrier it was.
+// Every barrier wait of this library therefore goes through b2l_wait_slow() once its first probe fails: after
+// `limit_ns` of wall time (default 4 s, env B2L_HANG_MS; decode kernels take microseconds) the waiting thread
+// writes {file hash, line, block, thread, barrier address, parity} into a host-pinned record and traps, which
+// turns the hang into a CUDA error the host reports with the record (b2l_hang_report()).  The fast path (the
+// probe succeeds) costs nothing; the slow path reads %globaltimer once per failed probe (each probe already
+// suspends the warp for up to 10 ms).
+struct B2lHangCtl {
+  unsigned int* rec;              // host-pinned, 16 words; null = watchdog disarmed
+  unsigned long long limit_ns;    // 0 = never trap
+  int taken;                      // first trapping thread of this translation unit writes the record
+};
+static __device__ B2lHangCtl b2l_hang_ctl = {nullptr, 0ull, 0};
+constexpr unsigned int b2l_file_hash(const char* s) {
+  unsigned int h = 2166136261u;
+  // hash of the basename only, so that build location does not matter
+  const char* base = s;
+  for (const char* c = s; *c; ++c)
+    if (*c == '/') base = c + 1;
+  for (const char* c = base; *c; ++c) h = (h ^ (unsigned char)*c) * 16777619u;
+  return h;
+}
+__device__ __forceinline__ unsigned long long b2l_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void b2l_hang_trap(uint32_t bar_addr, uint32_t parity, unsigned int file_hash, int line,
+                                           unsigned long long waited_ns) {
+  unsigned int* rec = b2l_hang_ctl.rec;
+  if (rec != nullptr && atomicCAS(&b2l_hang_ctl.taken, 0, 1) == 0) {
+    rec[1] = file_hash; rec[2] = (unsigned)line;
+    rec[3] = blockIdx.x; rec[4] = blockIdx.y; rec[5] = blockIdx.z;
+    rec[6] = threadIdx.x; rec[7] = bar_addr; rec[8] = parity;
+    rec[9] = (unsigned)(waited_ns / 1000000ull);
+    rec[10] = gridDim.x; rec[11] = gridDim.y; rec[12] = gridDim.z; rec[13] = blockDim.x;
+    __threadfence_system();
+    rec[0] = 0xB2D00DEDu;          // "record valid"
+    __threadfence_system();
+  } else {
+    // give the record's writer time to reach host memory before this thread kills the context
+    const unsigned long long t0 = b2l_globaltimer();
+    while (b2l_globaltimer() - t0 < 2000000ull) {
+    }
+  }
+  __trap();
+}
+// mode 0: try_wait + long suspend hint, 1: test_wait polling, 2: try_wait with the default suspend window
+template <int MODE>
+__device__ __forceinline__ void b2l_wait_slow(uint64_t* bar, uint32_t parity, unsigned int file_hash, int line) {
+  const unsigned long long t0 = b2l_globaltimer();
+  for (;;) {
+    const bool ok = MODE == 0 ? mbar_try_wait(bar, parity)
+                  : MODE == 1 ? mbar_test_wait(bar, parity) : mbar_try_wait_short(bar, parity);
+    if (ok) return;
+    const unsigned long long lim = b2l_hang_ctl.limit_ns;
+    const unsigned long long dt = b2l_globaltimer() - t0;
+    if (lim != 0ull && dt > lim) b2l_hang_trap(smem_u32(bar), parity, file_hash, line, dt);
   }
 }
-// try_wait with the default (short, implementation-defined) suspend window instead of the long hint above
-__device__ __forceinline__ void mbar_wait_short(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, unsigned int file_hash, int line) {
+  if (mbar_try_wait(bar, parity)) return;
+  b2l_wait_slow<0>(bar, parity, file_hash, line);
 }
+__device__ __forceinline__ void mbar_wait_spin_at(uint64_t* bar, uint32_t parity, unsigned int file_hash, int line) {
+  if (mbar_test_wait(bar, parity)) return;
+  b2l_wait_slow<1>(bar, parity, file_hash, line);
+}
+__device__ __forceinline__ void mbar_wait_short_at(uint64_t* bar, uint32_t parity, unsigned int file_hash, int line) {
+  if (mbar_try_wait_short(bar, parity)) return;
+  b2l_wait_slow<2>(bar, parity, file_hash, line);
+}
+#define mbar_wait(bar, parity) mbar_wait_at((bar), (parity), b2l_file_hash(__FILE__), __LINE__)
+#define mbar_wait_spin(bar, parity) mbar_wait_spin_at((bar), (parity), b2l_file_hash(__FILE__), __LINE__)
+#define mbar_wait_short(bar, parity) mbar_wait_short_at((bar), (parity), b2l_file_hash(__FILE__), __LINE__)
 
 // ---- async-proxy fences --------------------------------------------------- //
 // Generic-proxy smem writes (st.shared) must be made visible to the async proxy
@@ -388,10 +457,33 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_wait_prior();
 }
 
+// Host side of the hang watchdog: every translation unit has its own copy of b2l_hang_ctl (no relocatable device
+// code), armed once per device from the first launch of one of its kernels outside a stream capture.
+unsigned int* b2l_hang_record_ptr();          // core.cu: the process-wide host-pinned record
+unsigned long long b2l_hang_limit_ns();       // core.cu: env B2L_HANG_MS (default 4000, 0 = off)
+static inline void b2l_hang_arm(cudaStream_t st) {
+  static bool armed[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || armed[dev]) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return;   // a synchronous symbol copy is not capturable: arm at the next eager launch
+  }
+  B2lHangCtl h;
+  h.rec = b2l_hang_record_ptr();
+  h.limit_ns = b2l_hang_limit_ns();
+  h.taken = 0;
+  if (cudaMemcpyToSymbolAsync(b2l_hang_ctl, &h, sizeof(h), 0, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    (void)cudaGetLastError();
+  armed[dev] = true;
+}
+
 // Host side: launch `kern` on `st`, with the PDL attribute unless the library switch is off.
 template <typename... KArgs, typename... Args>
 static inline cudaError_t b2l_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args&&... args) {
+  b2l_hang_arm(st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;

@@ -75,3 +75,33 @@ extern "C" int b2l_device_info(int* sm_count, int* cc_major, int* cc_minor, int*
   }
   return B2L_OK;
 }
+
+// ---- device-side hang watchdog: host half (common.cuh, "device-side hang watchdog") ----
+static unsigned int* g_hang_rec = nullptr;
+unsigned int* b2l_hang_record_ptr() {
+  if (!g_hang_rec) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 64 * sizeof(unsigned int), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    memset(p, 0, 64 * sizeof(unsigned int));
+    g_hang_rec = (unsigned int*)p;
+  }
+  return g_hang_rec;
+}
+unsigned long long b2l_hang_limit_ns() {
+  const char* e = getenv("B2L_HANG_MS");
+  long long ms = (e && e[0]) ? atoll(e) : 4000;
+  if (ms < 0) ms = 0;
+  return (unsigned long long)ms * 1000000ull;
+}
+// Copies the 16-word hang record (all zero = no kernel of this library has trapped in a barrier wait):
+// out[0] = 0xB2D00DED when valid, [1] = FNV-1a hash of the source file's basename, [2] = line of the wait,
+// [3..5] = blockIdx, [6] = threadIdx.x, [7] = shared-memory address of the barrier, [8] = parity waited for,
+// [9] = milliseconds waited, [10..12] = gridDim, [13] = blockDim.x.  Readable after the context has died.
+extern "C" int b2l_hang_report(int* out16) {
+  B2L_REQUIRE(out16, "hang_report: null pointer");
+  for (int i = 0; i < 16; ++i) out16[i] = g_hang_rec ? (int)g_hang_rec[i] : 0;
+  return B2L_OK;
+}

@@ -38,8 +38,6 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int kb0 = split * p.kb_per_split;
   const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
   const int nkb = kb1 - kb0;
-  pdl_launch_dependents();   // the next kernel may set itself up while this one streams weights (common.cuh)
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
@@ -58,6 +56,10 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // The next kernel may set itself up while this one streams weights (common.cuh).  Triggered only AFTER this CTA
+  // owns its tensor memory: a dependent CTA that became co-resident earlier could take the SM's TMEM columns and
+  // then park in griddepcontrol.wait for this grid to finish -- while this CTA blocks in tcgen05.alloc (deadlock).
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================

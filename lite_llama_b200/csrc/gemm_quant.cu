@@ -83,12 +83,15 @@ enum { DBG_FORCE_XSUM = 8, DBG_RAW_OPERAND = 16, DBG_PAIR_K4 = 32, DBG_NO_STREAM
        DBG_FEW_MMA = 256 /* issue 1 of every 4 MMAs */, DBG_NO_STTM = 512 /* skip the TMEM operand store */,
        DBG_WAIT_SPIN = 1024 /* mbarrier.test_wait polling */, DBG_WAIT_SHORT = 2048 /* try_wait without the long suspend hint */,
        DBG_NO_XLOAD = 4096 /* activation tiles are never fetched */, DBG_HALF_RING = 8192 /* half the weight ring depth */,
+       DBG_LEGACY_OPRING = 16384 /* round-1 operand-ring indexing (phase-aliasing hang repro; results may be wrong) */,
        DBG_FORCE = 32768 /* no experiment: just run the DBG instantiation (prices its code size) */ };
-__device__ __forceinline__ void qwait(uint64_t* bar, uint32_t parity, int debug) {
-  if (debug & DBG_WAIT_SPIN) mbar_wait_spin(bar, parity);
-  else if (debug & DBG_WAIT_SHORT) mbar_wait_short(bar, parity);
-  else mbar_wait(bar, parity);
+__device__ __forceinline__ void qwait_at(uint64_t* bar, uint32_t parity, int debug, int line) {
+  constexpr unsigned int fh = b2l_file_hash(__FILE__);
+  if (debug & DBG_WAIT_SPIN) mbar_wait_spin_at(bar, parity, fh, line);
+  else if (debug & DBG_WAIT_SHORT) mbar_wait_short_at(bar, parity, fh, line);
+  else mbar_wait_at(bar, parity, fh, line);
 }
+#define qwait(bar, parity, debug) qwait_at((bar), (parity), (debug), __LINE__)
 constexpr int kTlCta = 4096;    // timeline: [1024][3] per-CTA {globaltimer at entry, at exit, SM id}
 constexpr int kTlSub = 3072 + 32;   // timeline: [96][5] per-sub-block stamps of dequant warp 0
 constexpr int kTlMisc = 3072;   // timeline: start-up / shutdown stamps of CTA (0,0,0), see tools/timeline.py
@@ -266,22 +269,46 @@ __device__ __forceinline__ void st_release_smem(int* p, int v) {
 // cycles, so its instruction count -- not the tensor pipe (16 cycles per MMA at 32 tokens: tools/mma_rate.cu) --
 // sets the pace of the accumulator hand-offs: ~25 instructions per sub-block here against ~90 in a rolled loop
 // with run-time stage arithmetic (700 cycles per segment on the device timeline, profiles/).
+// Operand-ring slot of operand stage `sp` (0 .. SUBST-1) of raw block `rb`.  The ring is split into two halves of
+// NST/2 stages: even raw blocks (dequant warps 0-3, MMA warp 0) cycle through the first half, odd raw blocks
+// (dequant warps 4-7, MMA warp 1) through the second.  Every op_full / op_empty barrier is then produced and
+// waited on by ONE dequant group and ONE MMA warp which both see every one of its phases in order.  (Round 1
+// indexed the ring as (2*rb + sp) % 6: a stage alternated between the two groups, so a waiter skipped every
+// other phase of "its" barrier and a parity wait could be satisfied by the completion of the phase BEFORE the
+// one it needed whenever one group ran a raw block ahead of the other -- stale operands, extra arrivals and,
+// eventually, a dead-locked pipeline: the intermittent decode hangs at 16- and 32-token tiles.)
+template <int NST, int SUBST>
+__device__ __forceinline__ void op_slot(int rb, int sp, int& stage, uint32_t& parity, int debug) {
+  constexpr int H = NST / 2;
+  static_assert(NST % 2 == 0 && H >= 1, "operand ring must split into two halves");
+  if (debug & DBG_LEGACY_OPRING) {            // round-1 indexing, kept in the DBG instantiation to reproduce the hang
+    const int gst = rb * SUBST + sp;
+    stage = gst % NST;
+    parity = (uint32_t)(gst / NST) & 1u;
+    return;
+  }
+  const int u = (rb >> 1) * SUBST + sp;       // running operand-stage count of this raw block's group
+  const int q = u / H;
+  stage = (rb & 1) * H + (u - q * H);
+  parity = (uint32_t)q & 1u;
+}
+
 template <int QK, int BT, int NST, int SPS>
 __device__ __forceinline__ void issue_block(QControl* ctl, uint32_t tmem_base, uint32_t a_base, uint64_t bdesc0,
-                                            int seg0, int gst0, uint64_t* x_empty, int debug) {
+                                            int seg0, int rb, uint64_t* x_empty, int debug) {
   constexpr int RW = raw_sub<QK>();
   constexpr int NB = 4;
   constexpr int kXBytes = BT * kStageKBytes;
   constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
 #pragma unroll
   for (int sp = 0; sp < RW / 2; ++sp) {
-    const int gst = gst0 + sp;
-    const int ostage = gst % NST;
+    int ostage; uint32_t oparity;
+    op_slot<NST, RW / 2>(rb, sp, ostage, oparity, debug);
     // segments touched by this stage: sub-blocks 2sp and 2sp+1
     const int segA = seg0 + (2 * sp) / SPS, segB = seg0 + (2 * sp + 1) / SPS;
     if ((2 * sp) % SPS == 0) qwait(&ctl->acc_empty[segA & (NB - 1)], ((segA / NB) & 1) ^ 1, debug);
     if (SPS == 1) qwait(&ctl->acc_empty[segB & (NB - 1)], ((segB / NB) & 1) ^ 1, debug);
-    qwait(&ctl->op_full[ostage], (gst / NST) & 1, debug);
+    qwait(&ctl->op_full[ostage], oparity, debug);
     tc_fence_after();
     if (elect_one()) {
       const uint32_t a_addr = a_base + ostage * 64;
@@ -384,7 +411,6 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   // two MMA warps (alternate raw blocks) when no segment spans two raw blocks, else warp 1 alone
   const int mma_warps = p.aligned ? 2 : 1;
 
-  pdl_launch_dependents();   // the next kernel may set itself up while this one streams weights (common.cuh)
   if (tl && threadIdx.x == 0) tl[kTlMisc + 0] = clock64();
   // every CTA: wall-clock (globaltimer, ns) at entry and exit + its SM id -> who is the straggler, and what is the
   // real SM clock (CTA 0 also stamps clock64 at both ends)
@@ -574,6 +600,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const bool cta_need_xsum = __syncthreads_or(bad_zero) != 0;
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // The next kernel may set itself up while this one streams weights (common.cuh) -- triggered only now that this
+  // CTA owns its tensor memory: a dependent CTA that became co-resident before the allocation could take the
+  // SM's TMEM columns and park in griddepcontrol.wait for this grid, while this CTA blocks in tcgen05.alloc.
+  pdl_launch_dependents();
   if (tl && threadIdx.x == 0) tl[kTlMisc + 1] = clock64();
 
   if (warp == kWarpWProd) {
@@ -633,20 +663,19 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const uint64_t bdesc0 = x_desc0 + (uint64_t)((rstage * kXStage) >> 4);
         if (mma_warps == 2 && steps_here == RW * 4) {
           // aligned mode: the raw block holds 1 or 2 whole segments
-          const int gst0 = gsub0 >> 1;
           if (seg_steps == RW * 4)
-            issue_block<QK, BT, OPS, RW>(ctl, tmem_base, a_base, bdesc0, seg, gst0, &ctl->x_empty[rstage], debug);
+            issue_block<QK, BT, OPS, RW>(ctl, tmem_base, a_base, bdesc0, seg, rb, &ctl->x_empty[rstage], debug);
           else
-            issue_block<QK, BT, OPS, RW / 2>(ctl, tmem_base, a_base, bdesc0, seg, gst0, &ctl->x_empty[rstage], debug);
+            issue_block<QK, BT, OPS, RW / 2>(ctl, tmem_base, a_base, bdesc0, seg, rb, &ctl->x_empty[rstage], debug);
         } else if (elect_one()) {
 #pragma unroll
           for (int st = 0; st < RW * 4; ++st) {
             if (st < steps_here) {
               const int buf = seg % NB;
-              const int gst = (gsub0 + (st >> 2)) >> 1;          // operand stage = two sub-blocks (gsub0 is even)
-              const int ostage = gst % kOpStages;
+              int ostage; uint32_t oparity;                      // operand stage = two sub-blocks
+              op_slot<kOpStages, RW / 2>(rb, st >> 3, ostage, oparity, debug);
               if ((st & 7) == 0) {
-                qwait(&ctl->op_full[ostage], (gst / kOpStages) & 1, debug);   // dequantised stage
+                qwait(&ctl->op_full[ostage], oparity, debug);   // dequantised stage
                 tc_fence_after();
               }
               if (!seg_open) {
@@ -909,10 +938,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         long long* const tls = (DBG && tl && warp == 0 && lane == 0 && gsub < 96) ? tl + kTlSub + gsub * 5 : nullptr;
         if (tls) tls[0] = clock64();
         if (gsub < nsub_total) {                               // sub-blocks past the k-range have no MMA step
-          const int gst = gsub >> 1;                           // operand stage = sub-blocks (2i, 2i+1); rb * RW is even
-          const int ostage = gst % kOpStages;
+          int ostage; uint32_t oparity;                        // operand stage = sub-blocks (2i, 2i+1); rb * RW is even
+          op_slot<kOpStages, RW / 2>(rb, sub >> 1, ostage, oparity, debug);
           if ((sub & 1) == 0) {
-            qwait(&ctl->op_empty[ostage], ((gst / kOpStages) & 1) ^ 1, debug);
+            qwait(&ctl->op_empty[ostage], oparity ^ 1, debug);
             tc_fence_after();
           }
           if (tls) tls[1] = clock64();

@@ -92,7 +92,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, blk = blockIdx.y;
-  pdl_prologue();                                   // num_post / expert_ids / sorted ids are the align kernel's output
+  pdl_wait_prior();                                 // num_post / expert_ids / sorted ids are the align kernel's output
   const int num_post = *p.num_post;
   if (blk * BT >= num_post) return;                 // whole CTA: nothing routed to this block
   const int expert = p.expert_ids[blk];
@@ -124,6 +124,9 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // dependents are released only once this CTA owns its tensor memory (a CTA that returned above counts as
+  // triggered): see gemm_dense.cu for the co-residency deadlock this ordering rules out
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer: this expert's weight tile =====================
