@@ -51,15 +51,15 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, kTmemCols);
     tmem_relinquish();
+    // The next kernel may set itself up while this one streams weights (common.cuh).  Only the TMEM-owning warp
+    // triggers, and only AFTER the allocation: a dependent CTA that became co-resident earlier could take the SM's
+    // TMEM columns and then park in griddepcontrol.wait for this grid -- while this CTA blocks in tcgen05.alloc.
+    pdl_launch_dependents();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-  // The next kernel may set itself up while this one streams weights (common.cuh).  Triggered only AFTER this CTA
-  // owns its tensor memory: a dependent CTA that became co-resident earlier could take the SM's TMEM columns and
-  // then park in griddepcontrol.wait for this grid to finish -- while this CTA blocks in tcgen05.alloc (deadlock).
-  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================

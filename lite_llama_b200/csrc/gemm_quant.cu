@@ -592,6 +592,11 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == kWarpMma0) {
     tmem_alloc(&ctl->tmem_base, kTmemCols);
     tmem_relinquish();
+    // The next kernel may set itself up while this one streams weights (common.cuh).  The CTA's trigger is issued by
+    // the warp that owns the tensor memory, AFTER the allocation: a dependent CTA that became co-resident before it
+    // could take the SM's TMEM columns and park in griddepcontrol.wait for this grid, while this CTA blocks in
+    // tcgen05.alloc (dead-lock).  No other warp triggers, so the CTA counts as triggered only from here on.
+    pdl_launch_dependents();
     if (tl && lane == 0) tl[kTlMisc + 9] = clock64();
   }
   if (tl && threadIdx.x == 0) tl[kTlMisc + 10] = clock64();
@@ -600,10 +605,6 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const bool cta_need_xsum = __syncthreads_or(bad_zero) != 0;
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-  // The next kernel may set itself up while this one streams weights (common.cuh) -- triggered only now that this
-  // CTA owns its tensor memory: a dependent CTA that became co-resident before the allocation could take the
-  // SM's TMEM columns and park in griddepcontrol.wait for this grid, while this CTA blocks in tcgen05.alloc.
-  pdl_launch_dependents();
   if (tl && threadIdx.x == 0) tl[kTlMisc + 1] = clock64();
 
   if (warp == kWarpWProd) {

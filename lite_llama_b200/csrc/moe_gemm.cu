@@ -119,14 +119,14 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, kTmemCols);
     tmem_relinquish();
+    // dependents are released by the TMEM-owning warp once the allocation is done (a CTA that returned above counts
+    // as triggered): see gemm_dense.cu for the co-residency dead-lock this ordering rules out
+    pdl_launch_dependents();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-  // dependents are released only once this CTA owns its tensor memory (a CTA that returned above counts as
-  // triggered): see gemm_dense.cu for the co-residency deadlock this ordering rules out
-  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer: this expert's weight tile =====================
