@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
+    ap.add_argument("--parallel", default="tp", choices=["tp", "dp"],
+                    help="N > 1: tp = ONE model sharded over the N GPUs (column/row-parallel projections, one exchange per "
+                         "row-parallel projection; strong scaling, same global batch); dp = N independent replicas "
+                         "(weak scaling, no collective)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-transformers-on-CPU row (configs[0])")
     ap.add_argument("--watchdog-s", type=int, default=600, help="give up (exit 3) after this many seconds; 0 = never")
@@ -54,12 +58,14 @@ def parse_args():
 
 
 def workload_config(args, world):
+    tp = world > 1 and getattr(args, "parallel", "tp") == "tp"
     return {
         "workload": f"{args.model} {'W4A16 g128' if args.quant == 'int4' else args.quant} greedy decode, "
-                    f"batch {args.batch}/GPU, prompt {args.prompt_len} -> {args.steps} new tokens "
+                    f"batch {args.batch}{'' if tp else '/GPU'}, prompt {args.prompt_len} -> {args.steps} new tokens "
                     f"(BASELINE.json configs[2]; the metric's named config)",
-        "model": args.model, "quant": args.quant, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
-        "prompt_len": args.prompt_len, "parallelism": f"dp{world}" if world > 1 else "single",
+        "model": args.model, "quant": args.quant, "per_gpu_batch": args.batch,
+        "global_batch": args.batch if tp else args.batch * world,
+        "prompt_len": args.prompt_len, "parallelism": (f"tp{world}" if tp else f"dp{world}") if world > 1 else "single",
         "l2_policy": "inputs_larger_than_l2 (4.98 GB of weights streamed per step vs 126 MB L2)",
         "cuda_graph": "one captured graph per decode step",
         "weight_layout": ("int4 tensors repacked once at load into the kernel-native layout (bit-exact nibble / table "
@@ -195,14 +201,17 @@ def run_reference(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use the host's cores whatever launched it
+    threads = os.cpu_count() or 1
+    steps = max(8, min(args.steps, 12))       # every timed step is a bounded sample; 8-12 of them keep the run short
     warm = max(1, min(args.warmup, 2))
-    base = cpu_decode_sample(args, steps, warm)
+    base = cpu_decode_sample(args, steps, warm, threads=threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step_full_model"],
+        "steps": steps, "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": base["ms_per_step_full_model"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world),     # the same workload description as this framework's arm at N GPUs
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": f"CPU port of the reference decode path; each of the {steps} timed steps is a bounded sample "
@@ -309,9 +318,18 @@ def main() -> None:
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    tp = world > 1 and args.parallel == "tp"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+        if tp:
+            # one model over all ranks: NCCL group + the NVLink peer-memory communicator of the fused exchange kernel
+            from lite_llama_b200.distributed import init_tensor_parallel
+
+            init_tensor_parallel()
+        else:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    # TP ranks hold shards of ONE model and step the SAME batch: identical seeds; DP replicas differ
+    seed = 0 if tp else rank
 
     from lite_llama_b200 import _lib
     from lite_llama_b200.executor import ModelRunner
@@ -326,7 +344,7 @@ def main() -> None:
     max_seq_len = max(bucket, total_len)
     t_build = time.time()
     runner = ModelRunner.build(args.model, max_seq_len=max_seq_len, max_gpu_num_blocks=B * max_seq_len, device=dev,
-                               quantization=None if args.quant == "fp16" else args.quant, seed=rank,
+                               quantization=None if args.quant == "fp16" else args.quant, seed=seed,
                                num_layers=args.layers)
     # capture the public-API decode graph before any KV is live (its warm-up writes dummy rows)
     runner.enable_cuda_graph(batch_sizes=(B,), seq_len_buckets=(bucket,))
@@ -335,7 +353,7 @@ def main() -> None:
     cfg = runner.config
     weight_bytes = runner.model.w.nbytes_per_step()
 
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + seed)
     prompts = torch.randint(0, cfg.vocab_size, (B, P), generator=gen, device=dev)
     lens = torch.full((B,), P, dtype=torch.int64, device=dev)
     b_req_idx = torch.arange(B, dtype=torch.int64, device=dev)
@@ -427,6 +445,35 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
 
+    # ---- tensor parallel: what one exchange costs (all ranks take part) ----
+    tp_info = None
+    if tp:
+        from lite_llama_b200.distributed import all_reduce_tp, get_tp_comm
+        from lite_llama_b200.kernels import skip_rmsnorm
+        from lite_llama_b200.kernels.tp_fused import allreduce_skip_rmsnorm
+
+        xx = torch.randn(B, cfg.hidden_size, device=dev, dtype=torch.float16)
+        rr = torch.randn(B, cfg.hidden_size, device=dev, dtype=torch.float16)
+        ww = torch.ones(cfg.hidden_size, device=dev, dtype=torch.float16)
+        calls = 64
+        dist.barrier()
+        us_fused = time_graph(lambda: [allreduce_skip_rmsnorm(xx, rr, ww) for _ in range(calls)]) * 1e3 / calls
+        dist.barrier()
+        us_nccl = time_graph(lambda: [skip_rmsnorm(all_reduce_tp(xx), rr, ww) for _ in range(calls)]) * 1e3 / calls
+        t = torch.tensor([us_fused, us_nccl], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_ex = 2 * cfg.num_layers
+        msg = B * cfg.hidden_size * 2
+        tp_info = {
+            "exchange": ("one kernel per row-parallel projection: push partial rows to every peer over NVLink, sum in rank "
+                         "order, residual add + RMSNorm (csrc/tp_comm.cu)") if get_tp_comm() is not None
+                        else "NCCL all-reduce + skip_rmsnorm (NVLink communicator unavailable)",
+            "nvlink_comm": get_tp_comm() is not None, "exchanges_per_step": n_ex, "message_bytes": msg,
+            "us_per_exchange_fused": float(t[0].item()), "us_per_nccl_allreduce_plus_rmsnorm": float(t[1].item()),
+            "exchange_share_of_step": float(t[0].item()) * n_ex / (dev_ms / K * 1e3),
+            "limiting_collective": f"{n_ex} latency-bound {msg // 1024} KiB exchanges per step",
+        }
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -434,14 +481,15 @@ def main() -> None:
         return
 
     hbm_peak, tf_peak, peak_src = peaks()
-    value = world * B * K / (dev_ms / 1e3)
-    e2e_value = world * B * K / (e2e_ms / 1e3)
+    replicas = 1 if tp else world
+    value = replicas * B * K / (dev_ms / 1e3)
+    e2e_value = replicas * B * K / (e2e_ms / 1e3)
     mean_ctx = P + W + (K + 1) / 2
     kv_bytes_step = B * mean_ctx * 2 * runner.num_kv_heads * cfg.head_dim * 2 * cfg.num_layers
     step_bytes = weight_bytes + kv_bytes_step
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
         "dtype": "f16 activations, int4 weights (fp32 accumulate)" if args.quant == "int4" else "f16",
         "data": "synthetic (random-init weights of the named shapes, random token ids)",
         "config": workload_config(args, world),
@@ -457,6 +505,8 @@ def main() -> None:
         "build_s": build_s,
         "sampled_token_checksum": int(tokens_dev.sum().item()),
     }
+    if tp_info is not None:
+        line["tensor_parallel"] = tp_info
     if not args.no_breakdown:
         try:
             kb = kernel_breakdown(runner, B, int(mean_ctx), hbm_peak)
@@ -474,7 +524,7 @@ def main() -> None:
                             "unit": "GB/s", "frac": line["step_roofline"]["frac"], "traffic": None}
     if not args.no_cpu_baseline and world == 1:      # reported baselines: rank 0 at N = 1 only
         try:
-            base = cpu_decode_sample(args, steps=3, warmup=1)
+            base = cpu_decode_sample(args, steps=8, warmup=1, threads=os.cpu_count() or 1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)[:300]}

@@ -199,6 +199,26 @@ int b2l_moe_sum(void* out, const void* in, int64_t tokens, int64_t n, int top_k,
 int b2l_moe_route_topk(void* topk_weights, void* topk_ids_i64, const void* router_logits, int64_t row_stride,
                        int64_t tokens, int num_experts, int top_k, int renormalize, int dtype, void* stream);
 
+/* ---- tensor-parallel exchange over NVLink peer memory (csrc/tp_comm.cu) ----
+ * Replaces all_reduce_tp (lite_llama/distributed/parallel_state.py:208-213: in-place NCCL SUM of the [tokens, hidden]
+ * partial after every row-parallel projection, lite_llama/models/linear.py:160-161, models/qwen3_moe.py:110) TOGETHER
+ * WITH the skip_rmsnorm that follows every one of them (lite_llama/models/base.py:307,312,486): one kernel pushes this
+ * rank's partial rows into every peer's receive buffer, waits for the peers' rows, sums in rank order (fp32, rounded to
+ * the activation dtype like the all-reduce output) and applies residual += sum; y = rmsnorm(residual) * weight.
+ * One process per GPU: b2l_tp_comm_create allocates this rank's buffer (capacity max_rows x max_row_elems 16-bit
+ * elements per peer) and returns an opaque handle (0 on error); b2l_tp_comm_get_handle exports its CUDA IPC handle
+ * (b2l_tp_comm_handle_bytes() bytes); the caller all-gathers the handles (torch.distributed) and passes the rank-major
+ * concatenation to b2l_tp_comm_open.  weight == NULL: plain all-reduce, y = sum.  Every rank must issue the same call
+ * sequence.  Graph-capturable (the double-buffer epoch lives in device memory). */
+int64_t b2l_tp_comm_create(int rank, int world, int max_rows, int64_t max_row_elems);
+int b2l_tp_comm_handle_bytes(void);
+int b2l_tp_comm_get_handle(int64_t comm, void* out, int64_t out_bytes);
+int b2l_tp_comm_open(int64_t comm, const void* handles, int64_t handles_bytes);
+int b2l_tp_comm_destroy(int64_t comm);
+int b2l_tp_allreduce_skip_rmsnorm(int64_t comm, void* y, const void* x_partial, void* residual, const void* weight,
+                                  int64_t rows, int64_t n, int64_t x_row_stride, int64_t r_row_stride,
+                                  int64_t y_row_stride, float eps, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

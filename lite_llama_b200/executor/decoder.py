@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from ..distributed import all_reduce_tp, divide, get_tp_rank, get_tp_world_size
+from ..distributed import divide, get_tp_rank, get_tp_world_size
 from ..kernels import (
     flash_attention2_no_pad,
     flash_decoding,
@@ -30,6 +30,7 @@ from ..kernels import (
     swiglu_forward,
     update_kv_buffer,
 )
+from ..kernels.tp_fused import allreduce_skip_rmsnorm
 from ..quantization import LinearWeights, apply_linear, make_linear_weights
 from .model_config import ModelConfig
 
@@ -149,8 +150,14 @@ class Decoder:
 
     # -- one decoder layer (base.py:299-319) ---------------------------------------------------
     def _layer(self, li: int, lw: LayerWeights, hidden, residual, atten_info, cos, sin, batch, seq_len):
+        """``hidden`` of every layer but the first is the previous layer's row-parallel down_proj output, i.e. a
+        per-rank PARTIAL under tensor parallelism: its all-reduce (linear.py:160-161) is fused into this layer's
+        input norm, the o_proj one into the post-attention norm (kernels/tp_fused.py)."""
         eps = self.cfg.rms_norm_eps
-        hidden, residual = skip_rmsnorm(hidden, residual, lw.input_norm, eps)          # base.py:307
+        if residual is None:
+            hidden, residual = skip_rmsnorm(hidden, residual, lw.input_norm, eps)      # base.py:307
+        else:
+            hidden, residual = allreduce_skip_rmsnorm(hidden, residual, lw.input_norm, eps)
         tokens = batch * seq_len
         x = hidden.view(tokens, self.cfg.hidden_size)
         qkv = apply_linear(x, lw.qkv)                                                   # base.py:213-215
@@ -177,12 +184,12 @@ class Decoder:
             attn = flash_decoding(xq, kv_buffer[:, : self.num_kv_heads], kv_buffer[:, self.num_kv_heads :],
                                   self.scale, atten_info.b_req_tokens_table, atten_info.b_req_idx,
                                   atten_info.b_seq_len, atten_info.max_actual_seq_len)
-        o = apply_linear(attn.view(tokens, self.q_size), lw.o)                          # base.py:245
-        o = all_reduce_tp(o)                                                            # linear.py:160-161
-        hidden, residual = skip_rmsnorm(o.view(batch, seq_len, -1), residual, lw.post_norm, eps)  # base.py:312
+        o = apply_linear(attn.view(tokens, self.q_size), lw.o)                          # base.py:245 (partial)
+        # all-reduce (linear.py:160-161) + residual add + post-attention norm (base.py:312) in one kernel
+        hidden, residual = allreduce_skip_rmsnorm(o.view(batch, seq_len, -1), residual, lw.post_norm, eps)
         gu = apply_linear(hidden.view(tokens, -1), lw.gate_up)                          # base.py:263-264
         act = swiglu_forward(gu[:, : self.inter], gu[:, self.inter :])
-        down = all_reduce_tp(apply_linear(act, lw.down))
+        down = apply_linear(act, lw.down)                                               # partial: reduced by the next norm
         return down.view(batch, seq_len, -1), residual
 
     @torch.no_grad()
@@ -201,5 +208,6 @@ class Decoder:
             rows = torch.arange(batch, device=hidden.device)
             hidden = hidden[rows, last_token_index].unsqueeze(1)
             residual = residual[rows, last_token_index].unsqueeze(1)
-        hidden, _ = skip_rmsnorm(hidden.contiguous(), residual.contiguous(), self.w.final_norm, self.cfg.rms_norm_eps)
+        hidden, _ = allreduce_skip_rmsnorm(hidden.contiguous(), residual.contiguous(), self.w.final_norm,
+                                           self.cfg.rms_norm_eps)                       # base.py:486
         return linear(hidden, self.w.lm_head)                                           # base.py:489

@@ -22,7 +22,8 @@ def test_header_parses_and_declares_the_hot_path_ops():
         assert name in protos, f"{name} missing from the header"
     # every entry point that launches work takes the stream last
     for name, (ret, args) in protos.items():
-        if ret == "int" and name not in ("b2l_version", "b2l_device_info", "b2l_set_pdl", "b2l_hang_report"):
+        if ret == "int" and name not in ("b2l_version", "b2l_device_info", "b2l_set_pdl", "b2l_hang_report", "b2l_tp_comm_handle_bytes",
+                                          "b2l_tp_comm_get_handle", "b2l_tp_comm_open", "b2l_tp_comm_destroy"):
             assert args[-1] == "void*", f"{name} must end with the stream argument"
 
 

@@ -1,0 +1,187 @@
+"""Multi-GPU tensor-parallel checks, one process per GPU (torchrun):
+
+  1. the NVLink peer-memory all-reduce (csrc/tp_comm.cu) against an fp32 sum of the gathered partials, bit-identical
+     on every rank, and against NCCL's fp16 all-reduce within 1 fp16 ulp of the fp32 truth;
+  2. the fused all-reduce + skip_rmsnorm against (NCCL all-reduce -> skip_rmsnorm);
+  3. decoder logits at TP=N against TP=1 (same full-matrix draw, each rank keeps its shard), prefill and decode;
+  4. the captured greedy decode loop (NVLink exchange inside the CUDA graph): 200 replays, identical tokens on all ranks;
+  5. latency of the exchange: NVLink kernel vs NCCL, [32, 4096] fp16, 64 calls per graph.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/tp_check.py
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+from lite_llama_b200 import _lib  # noqa: E402
+from lite_llama_b200.distributed import (  # noqa: E402
+    destroy_tensor_parallel, get_tp_comm, get_tp_rank, get_tp_world_size, init_tensor_parallel, parallel_state)
+
+
+def graph_time_us(fn, calls):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    ts = []
+    for _ in range(7):
+        dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3 / calls)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    init_tensor_parallel()
+    rank, world = get_tp_rank(), get_tp_world_size()
+    out = {"rank": rank, "world": world, "nvlink_comm": get_tp_comm() is not None}
+    try:
+        import lite_llama_b200.kernels as K
+        from lite_llama_b200.kernels.tp_fused import allreduce_nvlink, allreduce_skip_rmsnorm
+        from lite_llama_b200.executor import ModelRunner
+        from lite_llama_b200.executor.model_runner import GreedyDecodeLoop
+
+        # ---- 1 + 2: op level ----
+        worst_sum, worst_nccl, worst_fused = 0.0, 0.0, 0.0
+        for rows, n in ((1, 4096), (32, 4096), (256, 3584), (7, 2048), (32, 8192)):
+            for it in range(3):
+                g = torch.Generator(device=dev).manual_seed(1000 * rank + it)
+                part = torch.randn(rows, n, device=dev, dtype=torch.float16, generator=g)
+                gathered = [torch.empty_like(part) for _ in range(world)]
+                dist.all_gather(gathered, part)
+                truth32 = sum(t.float() for t in gathered)          # rank order, fp32 (what the kernel does)
+                got = allreduce_nvlink(part.clone())
+                assert torch.equal(got, truth32.to(torch.float16)), f"nvlink all-reduce differs from the fp32 sum ({rows}x{n})"
+                every = [torch.empty_like(got) for _ in range(world)]
+                dist.all_gather(every, got)
+                assert all(torch.equal(every[0], t) for t in every), "ranks disagree on the all-reduce result"
+                nccl = part.clone()
+                dist.all_reduce(nccl)
+                worst_nccl = max(worst_nccl, float((nccl.float() - truth32).abs().max()))
+                worst_sum = max(worst_sum, float((got.float() - truth32).abs().max()))
+                # fused with the norm
+                gr = torch.Generator(device=dev).manual_seed(55 + it)      # residual / weight identical on all ranks
+                res = torch.randn(rows, n, device=dev, dtype=torch.float16, generator=gr)
+                w = torch.randn(n, device=dev, dtype=torch.float16, generator=gr) * 0.1 + 1.0
+                r1, r2 = res.clone(), res.clone()
+                y1, r1o = allreduce_skip_rmsnorm(part.clone(), r1, w, 1e-5)
+                y2, r2o = K.skip_rmsnorm(truth32.to(torch.float16), r2, w, 1e-5)
+                assert torch.equal(r1o, r2o), "fused residual differs"
+                assert torch.equal(y1, y2), "fused norm output differs"
+                worst_fused = max(worst_fused, float((y1.float() - y2.float()).abs().max()))
+        out.update(allreduce_vs_fp32_sum_max_abs=worst_sum, nccl_vs_fp32_sum_max_abs=worst_nccl, fused_vs_unfused_max_abs=worst_fused)
+
+        # ---- 3: decoder TP=N vs TP=1 ----
+        def logits_for(tp_on: bool, name, quant, layers):
+            saved = (parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM)
+            if not tp_on:
+                parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM = 1, 0, None
+            try:
+                B, P = 3, 12
+                runner = ModelRunner.build(name, max_seq_len=64, max_gpu_num_blocks=B * 64, device=dev, quantization=quant,
+                                           seed=0, num_layers=layers)
+                gen = torch.Generator().manual_seed(0)
+                ids = torch.randint(0, runner.config.vocab_size, (B, P), generator=gen).to(dev)
+                lens = torch.tensor([12, 7, 9], device=dev)
+                pos = torch.arange(P, device=dev).repeat(B, 1)
+                runner.prefill_alloc_kv_cache(P, lens.clone(), torch.arange(B, device=dev))
+                pre = runner.forward(ids, pos)
+                nxt = pre[torch.arange(B, device=dev), lens - 1].argmax(-1)
+                runner.decode_alloc_kv_cache(B)
+                dec = runner.forward(nxt.view(B, 1), lens.view(B, 1))
+                return pre.float(), dec.float()
+            finally:
+                parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM = saved
+
+        tp_err = {}
+        for name, quant, layers in (("tiny-llama", None, 2), ("tiny-llama", "int4", 2), ("llama-3-8b", "int4", 2)):
+            if name == "tiny-llama" and world > 2:
+                continue      # 2 kv heads
+            p1, d1 = logits_for(False, name, quant, layers)
+            pn, dn = logits_for(True, name, quant, layers)
+            e_pre = float((pn - p1).abs().max())
+            e_dec = float((dn - d1).abs().max())
+            tp_err[f"{name}/{quant}"] = {"prefill_max_abs": e_pre, "decode_max_abs": e_dec,
+                                         "logit_scale": float(p1.abs().max())}
+            # partial sums are rounded to fp16 per rank before the exchange: a few fp16 ulps of the hidden state
+            assert e_pre < 3e-2 and e_dec < 3e-2, f"TP={world} logits differ from TP=1: {tp_err}"
+        out["tp_vs_tp1"] = tp_err
+
+        # ---- 4: captured greedy loop with the exchange inside the graph ----
+        B, P = 4, 16
+        runner = ModelRunner.build("llama-3-8b", max_seq_len=512, max_gpu_num_blocks=B * 512, device=dev, quantization="int4",
+                                   seed=0, num_layers=2)
+        gen = torch.Generator().manual_seed(3)
+        prompts = torch.randint(0, runner.config.vocab_size, (B, P), generator=gen).to(dev)
+        lens = torch.full((B,), P, dtype=torch.int64, device=dev)
+        req = torch.arange(B, dtype=torch.int64, device=dev)
+        runner.prefill_alloc_kv_cache(P, lens.clone(), req)
+        first = runner.forward(prompts, torch.arange(P, device=dev).repeat(B, 1), last_token_index=lens - 1)[:, -1].argmax(-1)
+        loop = GreedyDecodeLoop(runner, B, 512)
+        loop.begin(first, lens, req, runner.kv_cache_manager._bump_cursor)
+        loop.capture()
+        toks = []
+        for _ in range(200):
+            loop.step()
+            toks.append(loop.next_tokens.clone())
+        torch.cuda.synchronize()
+        toks = torch.stack(toks)
+        every = [torch.empty_like(toks) for _ in range(world)]
+        dist.all_gather(every, toks)
+        assert all(torch.equal(every[0], t) for t in every), "ranks sampled different tokens"
+        out["graph_loop_steps"] = 200
+
+        # ---- 5: latency ----
+        x = torch.randn(32, 4096, device=dev, dtype=torch.float16)
+        res = torch.randn(32, 4096, device=dev, dtype=torch.float16)
+        w = torch.ones(4096, device=dev, dtype=torch.float16)
+        out["us_nvlink_allreduce_32x4096"] = graph_time_us(lambda: [allreduce_nvlink(x) for _ in range(64)], 64)
+        out["us_nvlink_allreduce_rmsnorm_32x4096"] = graph_time_us(lambda: [allreduce_skip_rmsnorm(x, res, w) for _ in range(64)], 64)
+        out["us_nccl_allreduce_32x4096"] = graph_time_us(lambda: [dist.all_reduce(x) for _ in range(64)], 64)
+        out["us_nccl_allreduce_plus_rmsnorm_32x4096"] = graph_time_us(
+            lambda: [K.skip_rmsnorm(parallel_state.all_reduce_tp(x), res, w) for _ in range(64)], 64)
+        x1 = torch.randn(1, 4096, device=dev, dtype=torch.float16)
+        out["us_nvlink_allreduce_1x4096"] = graph_time_us(lambda: [allreduce_nvlink(x1) for _ in range(64)], 64)
+        out["us_nccl_allreduce_1x4096"] = graph_time_us(lambda: [dist.all_reduce(x1) for _ in range(64)], 64)
+        out["ok"] = True
+    except Exception as ex:
+        import traceback
+
+        out["ok"] = False
+        out["error"] = repr(ex)[:500]
+        out["trace"] = traceback.format_exc()[-1500:]
+        try:
+            out["hang"] = _lib.hang_report()
+        except Exception:
+            pass
+    print(json.dumps(out), flush=True)
+    if out["ok"]:
+        dist.barrier()
+        destroy_tensor_parallel()
+        sys.exit(0)
+    os._exit(1)
+
+
+if __name__ == "__main__":
+    main()
