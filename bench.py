@@ -383,10 +383,8 @@ def main() -> None:
 
     # ---- device-resident decode: one captured graph per step, zero host work ----
     loop = GreedyDecodeLoop(runner, B, bucket)
-    first_row = runner.kv_cache_manager._bump_cursor
-    loop.begin(first, lens, b_req_idx, first_row)
+    loop.begin(first, lens, b_req_idx, max_steps=K + W + 1)      # reserves its KV rows through the allocator
     loop.capture()
-    runner.kv_cache_manager.claim(first_row + B * (K + W + 1))
     for _ in range(W):
         loop.step()
     torch.cuda.synchronize()

@@ -26,9 +26,20 @@ from .attention_metadata import AttentionMetadata
 from .decoder import Decoder, DecoderWeights, random_weights
 from .kv_cache_manager import KVCacheManager
 from .model_config import PRESETS, ModelConfig
+from .slot_batch import SlotBatch
 
-DEFAULT_BATCH_SIZES = (1, 2, 4, 8, 16, 32, 64, 128)          # executor/cuda_graph.py:27
+# executor/cuda_graph.py:27 stops at 128; 256 added so that a 256-wide continuous batch (BASELINE configs[3]) stays
+# on the graph path
+DEFAULT_BATCH_SIZES = (1, 2, 4, 8, 16, 32, 64, 128, 256)
 DEFAULT_SEQ_LEN_BUCKETS = (256, 512, 1024, 2048, 4096)       # executor/cuda_graph.py:28
+
+
+class ModelSpec:
+    """What the engines ask about an architecture (reference: lite_llama/models/registry.py:24-40)."""
+
+    def __init__(self, model_type: str, is_multimodal: bool = False) -> None:
+        self.model_type = model_type
+        self.is_multimodal = is_multimodal
 
 
 class _CapturedDecode:
@@ -99,6 +110,8 @@ class GreedyDecodeLoop:
             max_actual_seq_len=bucket)
         self.graph: torch.cuda.CUDAGraph | None = None
         self.launches_per_step = 0
+        self._steps_left = 0          # host-side bound: rows reserved for the loop / room left in the bucket
+        self._reserved: tuple[int, int] | None = None      # (first row, steps) handed out by begin()
 
     def _step_ops(self) -> None:
         # state on entry: input_ids = last sampled token, b_seq_len = history length INCLUDING it,
@@ -111,9 +124,30 @@ class GreedyDecodeLoop:
         self.b_seq_len.add_(1)
         self.cur_select_index.add_(self.batch)
 
-    def begin(self, last_tokens: torch.Tensor, seq_lens: torch.Tensor, b_req_idx: torch.Tensor, first_row: int) -> None:
+    def begin(self, last_tokens: torch.Tensor, seq_lens: torch.Tensor, b_req_idx: torch.Tensor,
+              first_row: int | None = None, max_steps: int | None = None) -> None:
         """Seed the loop after prefill: ``last_tokens`` are the first sampled tokens, ``seq_lens`` the
-        prompt lengths (the history length becomes ``seq_lens + 1`` once the token is appended)."""
+        prompt lengths (the history length becomes ``seq_lens + 1`` once the token is appended).
+
+        The loop advances its KV cursor on the device, so its rows are reserved HERE, through the allocator:
+        ``max_steps`` steps need ``batch * max_steps`` consecutive rows (``first_row=None``); ``step()`` refuses to
+        run past them or past the graph's seq-len bucket. Passing ``first_row`` re-seeds a loop on rows reserved
+        by an earlier ``begin`` (the stress test replays one reservation many times)."""
+        longest = int(seq_lens.max().item()) + 1
+        room = self.bucket - longest + 1               # steps until a history would exceed the bucket
+        if first_row is None:
+            if max_steps is None:
+                raise ValueError("begin() needs max_steps to reserve the loop's KV rows")
+            rows = self.runner.kv_cache_manager.alloc_kvcache_index(self.batch * max_steps)
+            if rows is None:
+                raise RuntimeError(f"KV cache exhausted: the loop needs {self.batch * max_steps} rows")
+            first_row = int(rows[0].item())
+            if int(rows[-1].item()) - first_row != rows.numel() - 1:
+                raise RuntimeError("the loop needs consecutive KV rows (allocate it before any partial free)")
+            self._reserved = (first_row, max_steps)
+        elif self._reserved is None or self._reserved[0] != first_row:
+            self._reserved = (first_row, max_steps if max_steps is not None else room)   # caller-managed rows
+        self._steps_left = max(0, min(self._reserved[1], room))
         self.input_ids.copy_(last_tokens.view(-1, 1))
         self.b_seq_len.copy_((seq_lens + 1).to(torch.int32))
         self.position_ids.copy_(seq_lens.view(-1, 1).to(torch.int64))
@@ -142,6 +176,10 @@ class GreedyDecodeLoop:
         # capture does not execute: the state tensors still hold the snapshot
 
     def step(self) -> None:
+        if self._steps_left <= 0:
+            raise RuntimeError("GreedyDecodeLoop.step(): past the KV rows reserved by begin() or past the seq-len bucket "
+                               f"({self.bucket}); nothing was launched")
+        self._steps_left -= 1
         self.graph.replay()
 
 
@@ -167,6 +205,8 @@ class ModelRunner:
         self.atten_info.kv_buffer = self.kv_cache_manager.gpu_kv_buffer
         self.atten_info.b_req_tokens_table = self.b_req_tokens_table
         self.model = Decoder(config, weights, max_pos=self.max_seq_len, device=device, dtype=dtype)
+        self.spec = ModelSpec(config.name)
+        self._slot_batch: SlotBatch | None = None
         self._graphs: dict[tuple[int, int], _CapturedDecode] = {}
         self._graph_batches: tuple[int, ...] = ()
         self._graph_buckets: tuple[int, ...] = ()
@@ -236,6 +276,10 @@ class ModelRunner:
         batch_sizes = tuple(b for b in batch_sizes if b <= self.max_request_num)
         if not seq_len_buckets or not batch_sizes:
             return
+        if self.kv_cache_manager.can_use_mem_size != self.kv_cache_manager.max_num_tokens:
+            # the capture warm-up writes dummy K/V through row 0 of request 0 (like the reference's,
+            # executor/cuda_graph.py:100-119): with live rows that would clobber a request's first token
+            raise RuntimeError("enable_cuda_graph() must run before any KV rows are allocated (its warm-up writes row 0)")
         try:
             for b in batch_sizes:
                 for s in seq_len_buckets:
@@ -246,6 +290,14 @@ class ModelRunner:
             return
         self._graph_batches = tuple(sorted({k[0] for k in self._graphs}))
         self._graph_buckets = tuple(sorted({k[1] for k in self._graphs}))
+
+    def enable_slot_kv_cache(self) -> SlotBatch:
+        """Switch the KV pool to the fixed-slot layout continuous batching uses (model_runner.py:221-234).
+        Idempotent; mutually exclusive with the one-shot ``*_alloc_kv_cache`` path (the slot table claims every
+        row it names). Call it after :meth:`enable_cuda_graph` so that batch padding sees the captured widths."""
+        if self._slot_batch is None:
+            self._slot_batch = SlotBatch(self)
+        return self._slot_batch
 
     def graph_batch_size(self, batch_size: int) -> int:
         for b in self._graph_batches:

@@ -110,6 +110,9 @@ def test_captured_decode_graph_equals_eager():
         return torch.stack(toks).cpu()
 
     eager = run(False)
+    with pytest.raises(RuntimeError):          # live KV rows: the capture warm-up would clobber row 0
+        runner.enable_cuda_graph(batch_sizes=(4,), seq_len_buckets=(256,))
+    runner.kv_cache_manager.free_all()
     runner.enable_cuda_graph(batch_sizes=(4,), seq_len_buckets=(256,))
     assert runner.graph_batch_size(3) == 4
     graphed = run(True)
@@ -141,7 +144,7 @@ def test_greedy_decode_loop_matches_step_by_step_api():
         p = p + 1
     first = prefill()
     loop = GreedyDecodeLoop(runner, B, 256)
-    loop.begin(first, lens, b_req, runner.kv_cache_manager._bump_cursor)
+    loop.begin(first, lens, b_req, max_steps=steps)
     loop.capture()
     got = []
     for _ in range(steps):
@@ -149,6 +152,8 @@ def test_greedy_decode_loop_matches_step_by_step_api():
         got.append(loop.next_tokens.cpu().clone())
     assert torch.equal(torch.stack(got), torch.stack(expect))
     assert loop.launches_per_step > 0
+    with pytest.raises(RuntimeError):      # the rows reserved by begin() are used up: nothing may be launched
+        loop.step()
 
 
 def test_programmatic_dependent_launch_is_bit_identical():
@@ -190,6 +195,7 @@ def test_programmatic_dependent_launch_is_bit_identical():
     assert torch.equal(serial, overlapped), "PDL changed a logit: a kernel touched upstream data before griddepcontrol.wait"
     old = lib.b2l_set_pdl(1)
     try:
+        runner.kv_cache_manager.free_all()        # capture refuses to run over live KV rows
         runner.enable_cuda_graph(batch_sizes=(4,), seq_len_buckets=(256,))   # graph nodes keep the attribute they were captured with
     finally:
         lib.b2l_set_pdl(old)

@@ -63,8 +63,8 @@ def main() -> int:
         first = logits[:, -1].argmax(-1)
         torch.cuda.synchronize()
         loop = GreedyDecodeLoop(runner, B, bucket)
-        first_row = runner.kv_cache_manager._bump_cursor
-        loop.begin(first, lens, b_req_idx, first_row)
+        loop.begin(first, lens, b_req_idx, max_steps=span)       # reserves span * B consecutive KV rows
+        first_row = loop._reserved[0]
         loop.capture()
         out["launches_per_step"] = loop.launches_per_step
 

@@ -139,7 +139,7 @@ def main():
         runner.prefill_alloc_kv_cache(P, lens.clone(), req)
         first = runner.forward(prompts, torch.arange(P, device=dev).repeat(B, 1), last_token_index=lens - 1)[:, -1].argmax(-1)
         loop = GreedyDecodeLoop(runner, B, 512)
-        loop.begin(first, lens, req, runner.kv_cache_manager._bump_cursor)
+        loop.begin(first, lens, req, max_steps=201)
         loop.capture()
         toks = []
         for _ in range(200):
