@@ -473,9 +473,7 @@ def main() -> None:
         }
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish(world)
         return
 
     hbm_peak, tf_peak, peak_src = peaks()
@@ -537,9 +535,24 @@ def main() -> None:
         except Exception as ex:
             line["hf_cpu_baseline"] = {"error": repr(ex)[:300]}
     print(json.dumps(line), flush=True)
-    if world > 1:
+    finish(world)
+
+
+def finish(world: int) -> None:
+    """Multi-rank exit: meet once more, then leave without tearing NCCL down -- destroying a process group while
+    captured graphs still hold its kernels can block for ever, and a bench that printed its line must not hang."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    try:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

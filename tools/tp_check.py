@@ -110,7 +110,9 @@ def main():
                 nxt = pre[torch.arange(B, device=dev), lens - 1].argmax(-1)
                 runner.decode_alloc_kv_cache(B)
                 dec = runner.forward(nxt.view(B, 1), lens.view(B, 1))
-                return pre.float(), dec.float()
+                # padded prefill positions (beyond a sequence's own length) hold unspecified values: compare valid rows only
+                valid = (torch.arange(P, device=dev)[None, :] < lens[:, None])
+                return pre.float()[valid], dec.float()
             finally:
                 parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM = saved
 
