@@ -203,7 +203,8 @@ int b2l_moe_route_topk(void* topk_weights, void* topk_ids_i64, const void* route
  * Replaces all_reduce_tp (lite_llama/distributed/parallel_state.py:208-213: in-place NCCL SUM of the [tokens, hidden]
  * partial after every row-parallel projection, lite_llama/models/linear.py:160-161, models/qwen3_moe.py:110) TOGETHER
  * WITH the skip_rmsnorm that follows every one of them (lite_llama/models/base.py:307,312,486): one kernel pushes this
- * rank's partial rows into every peer's receive buffer, waits for the peers' rows, sums in rank order (fp32, rounded to
+ * rank's partial rows into every peer's receive buffer as 16-byte {6 values, epoch} packets (no fence, no separate
+ * flag), polls the peers' packets in its own buffer, sums in rank order (fp32, rounded to
  * the activation dtype like the all-reduce output) and applies residual += sum; y = rmsnorm(residual) * weight.
  * One process per GPU: b2l_tp_comm_create allocates this rank's buffer (capacity max_rows x max_row_elems 16-bit
  * elements per peer) and returns an opaque handle (0 on error); b2l_tp_comm_get_handle exports its CUDA IPC handle

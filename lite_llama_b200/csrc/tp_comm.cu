@@ -10,28 +10,31 @@
 //
 // Here the two are ONE kernel over peer memory (one process per GPU, buffers exchanged once through CUDA IPC):
 //   push    each CTA owns one token row: it stores its rank's partial row straight into slot [rank] of every
-//           peer's receive buffer (posted NVLink writes, no round trip), fences, and raises a per-row flag on the peer;
-//   gather  it waits for the same-row flags of all peers, then sums the world_size partials from its OWN receive
-//           buffer in rank order (fp32; every rank adds in the same order -> bit-identical results on all ranks),
+//           peer's receive buffer as 16-byte packets {6 values, epoch} (posted NVLink writes: no round trip, no fence,
+//           no separate flag -- every packet carries its own validity word);
+//   gather  it polls the same-row packets of all peers in its OWN receive buffer and sums the world_size partials
+//           in rank order (fp32; every rank adds in the same order -> bit-identical results on all ranks),
 //           rounds to the activation dtype exactly where the reference's all-reduce output would be,
 //   norm    and runs skip_rmsnorm on it (same arithmetic and rounding points as elementwise.cu) while the row is
 //           still in registers: residual += sum; y = round(residual_f32 * rrms) * w.
-// Receive buffers and flags are double-buffered by an epoch each rank keeps per row in its own memory, so the
-// kernel needs no trailing barrier and is CUDA-graph capturable (no host state changes between replays): a peer can
-// only reach epoch e+2 (which reuses the parity of e) after this rank raised its flag for e+1, i.e. after it finished
-// reading epoch e.
+// Receive buffers are double-buffered by an epoch each rank keeps per row in its own memory, so the kernel needs
+// no trailing barrier and is CUDA-graph capturable (no host state changes between replays): a peer can only reach
+// epoch e+2 (which reuses the parity of e) after it received this rank's packets of e+1, which this rank sends after
+// it finished reading epoch e.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kMaxWorld = 8;
 constexpr int kThreads = 256;
-constexpr int kMaxChunksPerThread = 4;      // 16-byte chunks per thread: rows up to 256*4*8 = 8192 elements
+constexpr int kMaxIters = 6;                 // packets per thread: rows up to 256 * 6 * 6 = 9216 elements
+constexpr int kPktElems = 6;                 // a 16-byte packet = 6 activation values (3 words) + the epoch word
 
 struct CommState {
   int rank, world;
   int max_rows;
-  int64_t row_bytes;                         // capacity of one row slot
+  int64_t row_bytes;                         // capacity of one row slot (packets * 16)
+  int64_t max_row_elems;
   unsigned char* local;                      // this rank's allocation
   unsigned char* peer[kMaxWorld];            // peer[r] = mapped base of rank r's allocation (peer[rank] = local)
   cudaIpcMemHandle_t handle;
@@ -39,15 +42,13 @@ struct CommState {
 };
 
 // layout of one rank's allocation:
-//   [recv: 2 parities][world slots][max_rows][row_bytes]   data pushed by the peers
-//   [flags: 2 parities][max_rows][kMaxWorld] uint32        raised by the peers
+//   [recv: 2 parities][world slots][max_rows][row_bytes]   packets pushed by the peers
 //   [epoch: max_rows] uint32                               private to the owner
 __host__ __device__ inline int64_t recv_bytes(int world, int max_rows, int64_t row_bytes) {
   return 2ll * world * max_rows * row_bytes;
 }
-__host__ __device__ inline int64_t flags_bytes(int max_rows) { return 2ll * max_rows * kMaxWorld * 4; }
 __host__ __device__ inline int64_t total_bytes(int world, int max_rows, int64_t row_bytes) {
-  return recv_bytes(world, max_rows, row_bytes) + flags_bytes(max_rows) + (int64_t)max_rows * 4;
+  return recv_bytes(world, max_rows, row_bytes) + (int64_t)max_rows * 4;
 }
 
 struct FusedParams {
@@ -62,12 +63,15 @@ struct FusedParams {
   float eps;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Flag-in-data packets (the idea of NCCL's LL protocols): every 16-byte store carries its own validity word, so the
+// sender needs no fence and no separate flag write, and the receiver sees a packet one NVLink traversal after it was
+// stored.  A naturally aligned 16-byte store of one thread is delivered as a unit.
+__device__ __forceinline__ void st_pkt(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(flag) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_pkt(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ float sqrt_approx_f(float x) {
@@ -80,103 +84,118 @@ __device__ __forceinline__ float div_full_f(float a, float b) {
   asm("div.full.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+  const T* e = reinterpret_cast<const T*>(&w);
+  a = to_f32(e[0]); b = to_f32(e[1]);
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2t(float a, float b) {
+  uint32_t w;
+  T* e = reinterpret_cast<T*>(&w);
+  e[0] = from_f32<T>(a); e[1] = from_f32<T>(b);
+  return w;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) tp_allreduce_rmsnorm_kernel(const FusedParams p) {
   pdl_prologue();                              // the partial rows are the previous kernel's output
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
-  const int nchunks = p.n / 8;
+  const int nwords = p.n / 2;                  // 32-bit words per row
+  const int npkts = (nwords + 2) / 3;
   unsigned char* mine_base = p.peer[p.rank];
   const int64_t rbytes = recv_bytes(p.world, p.max_rows, p.row_bytes);
-  unsigned int* my_flags = reinterpret_cast<unsigned int*>(mine_base + rbytes);
-  unsigned int* my_epoch = reinterpret_cast<unsigned int*>(mine_base + rbytes + flags_bytes(p.max_rows));
+  unsigned int* my_epoch = reinterpret_cast<unsigned int*>(mine_base + rbytes);
   const unsigned int e = my_epoch[row] + 1u;   // same value on every rank: all ranks run the same call sequence
   const int par = (int)(e & 1u);
 
-  // ---- push this rank's partial row into slot [rank] of every peer ----
-  const T* xr = reinterpret_cast<const T*>(p.x) + (int64_t)row * p.x_stride;
-  uint4 mine[kMaxChunksPerThread];
+  // ---- push this rank's partial row, packet by packet, into slot [rank] of every peer ----
+  const uint32_t* xr = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(p.x) + (int64_t)row * p.x_stride);
+  uint32_t mine[kMaxIters][3];
 #pragma unroll
-  for (int i = 0; i < kMaxChunksPerThread; ++i) {
+  for (int i = 0; i < kMaxIters; ++i) {
     const int c = tid + i * kThreads;
-    mine[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (c < nchunks) mine[i] = ldg_128(xr + c * 8);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int wi = 3 * c + k;
+      mine[i][k] = (c < npkts && wi < nwords) ? __ldg(xr + wi) : 0u;
+    }
   }
   const int64_t slot_off = (((int64_t)par * p.world + p.rank) * p.max_rows + row) * p.row_bytes;
   for (int d = 1; d < p.world; ++d) {
     const int peer = (p.rank + d) % p.world;   // staggered so that the ranks do not all hit the same peer first
     unsigned char* dst = p.peer[peer] + slot_off;
 #pragma unroll
-    for (int i = 0; i < kMaxChunksPerThread; ++i) {
+    for (int i = 0; i < kMaxIters; ++i) {
       const int c = tid + i * kThreads;
-      if (c < nchunks) *reinterpret_cast<uint4*>(dst + (int64_t)c * 16) = mine[i];
+      if (c < npkts) st_pkt(dst + (int64_t)c * 16, mine[i][0], mine[i][1], mine[i][2], e);
     }
   }
-  __syncthreads();                             // every thread's stores precede the flag writers' fence
-  if (tid < p.world && tid != p.rank) {
-    __threadfence_system();
-    unsigned int* pf = reinterpret_cast<unsigned int*>(p.peer[tid] + rbytes) +
-                       ((int64_t)par * p.max_rows + row) * kMaxWorld + p.rank;
-    st_release_sys(pf, e);
-    // ---- wait for that peer's row ----
-    const unsigned int* wf = my_flags + ((int64_t)par * p.max_rows + row) * kMaxWorld + tid;
-    if (ld_acquire_sys(wf) != e) {
-      const unsigned long long t0 = b2l_globaltimer();
-      while (ld_acquire_sys(wf) != e) {
-        const unsigned long long lim = b2l_hang_ctl.limit_ns;
-        const unsigned long long dt = b2l_globaltimer() - t0;
-        if (lim != 0ull && dt > lim) b2l_hang_trap((uint32_t)tid, e, b2l_file_hash(__FILE__), __LINE__, dt);
-      }
-    }
-  }
-  __syncthreads();
 
-  // ---- sum the partials in rank order (fp32), round like the reference's fp16 all-reduce output ----
-  float vals[kMaxChunksPerThread][8];
+  // ---- gather: poll the peers' packets in this rank's own buffer, sum in rank order (fp32) ----
+  float vals[kMaxIters][kPktElems];
   float ss = 0.f;
   T* rr = p.res ? reinterpret_cast<T*>(p.res) + (int64_t)row * p.r_stride : nullptr;
   T* yr = reinterpret_cast<T*>(p.y) + (int64_t)row * p.y_stride;
 #pragma unroll
-  for (int i = 0; i < kMaxChunksPerThread; ++i) {
+  for (int i = 0; i < kMaxIters; ++i) {
     const int c = tid + i * kThreads;
-    if (c < nchunks) {
-      float acc[8];
+    if (c < npkts) {
+      float acc[kPktElems];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < kPktElems; ++j) acc[j] = 0.f;
       for (int r = 0; r < p.world; ++r) {
-        uint4 v;
+        uint32_t w3[3];
         if (r == p.rank) {
-          v = mine[i];
+          w3[0] = mine[i][0]; w3[1] = mine[i][1]; w3[2] = mine[i][2];
         } else {
-          const unsigned char* src = mine_base + (((int64_t)par * p.world + r) * p.max_rows + row) * p.row_bytes;
-          v = __ldcg(reinterpret_cast<const uint4*>(src + (int64_t)c * 16));
+          const unsigned char* src = mine_base + (((int64_t)par * p.world + r) * p.max_rows + row) * p.row_bytes + (int64_t)c * 16;
+          uint4 v = ld_pkt(src);
+          if (v.w != e) {
+            const unsigned long long t0 = b2l_globaltimer();
+            do {
+              v = ld_pkt(src);
+              const unsigned long long lim = b2l_hang_ctl.limit_ns;
+              const unsigned long long dt = b2l_globaltimer() - t0;
+              if (lim != 0ull && dt > lim && v.w != e) b2l_hang_trap((uint32_t)r, e, b2l_file_hash(__FILE__), __LINE__, dt);
+            } while (v.w != e);
+          }
+          w3[0] = v.x; w3[1] = v.y; w3[2] = v.z;
         }
-        const T* ve = reinterpret_cast<const T*>(&v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += to_f32(ve[j]);
+        for (int k = 0; k < 3; ++k) {
+          float a, b;
+          unpack2<T>(w3[k], a, b);
+          acc[2 * k] += a; acc[2 * k + 1] += b;
+        }
       }
-      uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-      if (rr) rv = ldg_128(rr + c * 8);
-      const T* re = reinterpret_cast<const T*>(&rv);
-      uint4 ov;
-      T* oe = reinterpret_cast<T*>(&ov);
+      uint32_t* rw = rr ? reinterpret_cast<uint32_t*>(rr) : nullptr;
+      uint32_t* yw = reinterpret_cast<uint32_t*>(yr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float o16 = to_f32(from_f32<T>(acc[j]));        // the all-reduce result in the activation dtype
-        const float s = rr ? o16 + to_f32(re[j]) : o16;        // skip_rmsnorm.py: r += x
-        vals[i][j] = s;
-        oe[j] = from_f32<T>(s);
-        ss += s * s;
+      for (int k = 0; k < 3; ++k) {
+        const int wi = 3 * c + k;
+        float s0 = 0.f, s1 = 0.f;
+        if (wi < nwords) {
+          // the all-reduce result in the activation dtype (what the reference's NCCL call leaves in the tensor) ...
+          const float o0 = to_f32(from_f32<T>(acc[2 * k])), o1 = to_f32(from_f32<T>(acc[2 * k + 1]));
+          s0 = o0; s1 = o1;
+          if (rw) {                                              // ... then skip_rmsnorm.py: r += x
+            float r0, r1;
+            unpack2<T>(rw[wi], r0, r1);
+            s0 += r0; s1 += r1;
+            rw[wi] = pack2t<T>(s0, s1);
+          } else if (!p.w) {
+            yw[wi] = pack2t<T>(s0, s1);                          // plain all-reduce
+          }
+        }
+        vals[i][2 * k] = s0; vals[i][2 * k + 1] = s1;
+        ss += s0 * s0 + s1 * s1;
       }
-      if (rr) stg_128(rr + c * 8, ov);
-      else if (!p.w) stg_128(yr + c * 8, ov);                  // plain all-reduce
     }
   }
   if (tid == 0) my_epoch[row] = e;
   if (!p.w) return;
 
-  // ---- RMSNorm of the row (same arithmetic as skip_rmsnorm_block_kernel) ----
+  // ---- RMSNorm of the row (skip_rmsnorm.py:126-189: fp32 mean of squares, round before the weight multiply) ----
   __shared__ float red[kThreads / 32];
   ss = warp_reduce_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
@@ -185,21 +204,22 @@ __global__ void __launch_bounds__(kThreads) tp_allreduce_rmsnorm_kernel(const Fu
 #pragma unroll
   for (int i = 0; i < kThreads / 32; ++i) tot += red[i];
   const float rrms = div_full_f(1.0f, sqrt_approx_f(tot / (float)p.n + p.eps));
-  const T* w = reinterpret_cast<const T*>(p.w);
+  const uint32_t* ww = reinterpret_cast<const uint32_t*>(p.w);
+  uint32_t* yw = reinterpret_cast<uint32_t*>(yr);
 #pragma unroll
-  for (int i = 0; i < kMaxChunksPerThread; ++i) {
+  for (int i = 0; i < kMaxIters; ++i) {
     const int c = tid + i * kThreads;
-    if (c < nchunks) {
-      uint4 wv = ldg_128(w + c * 8);
-      const T* we = reinterpret_cast<const T*>(&wv);
-      uint4 ov;
-      T* oe = reinterpret_cast<T*>(&ov);
+    if (c < npkts) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        T nrm = from_f32<T>(vals[i][j] * rrms);
-        oe[j] = from_f32<T>(to_f32(nrm) * to_f32(we[j]));
+      for (int k = 0; k < 3; ++k) {
+        const int wi = 3 * c + k;
+        if (wi < nwords) {
+          float w0, w1;
+          unpack2<T>(__ldg(ww + wi), w0, w1);
+          const float n0 = to_f32(from_f32<T>(vals[i][2 * k] * rrms)), n1 = to_f32(from_f32<T>(vals[i][2 * k + 1] * rrms));
+          yw[wi] = pack2t<T>(n0 * w0, n1 * w1);
+        }
       }
-      stg_128(yr + c * 8, ov);
     }
   }
 }
@@ -209,18 +229,20 @@ __global__ void __launch_bounds__(kThreads) tp_allreduce_rmsnorm_kernel(const Fu
 // ---- host side: one communicator per process (one process per GPU) ----
 extern "C" int64_t b2l_tp_comm_create(int rank, int world, int max_rows, int64_t max_row_elems) {
   if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || max_rows <= 0 || max_row_elems <= 0 ||
-      max_row_elems % 8 != 0 || max_row_elems > (int64_t)kThreads * kMaxChunksPerThread * 8) {
+      max_row_elems % 2 != 0 || max_row_elems > (int64_t)kThreads * kMaxIters * kPktElems) {
     b2l_set_error("tp_comm_create: bad arguments (world %d, rank %d, rows %d, row elems %lld; world <= %d, row elems <= %d)",
-                  world, rank, max_rows, (long long)max_row_elems, kMaxWorld, kThreads * kMaxChunksPerThread * 8);
+                  world, rank, max_rows, (long long)max_row_elems, kMaxWorld, kThreads * kMaxIters * kPktElems);
     return 0;
   }
   CommState* cs = new CommState();
   memset(cs, 0, sizeof(*cs));
-  cs->rank = rank; cs->world = world; cs->max_rows = max_rows; cs->row_bytes = max_row_elems * 2;
+  cs->rank = rank; cs->world = world; cs->max_rows = max_rows; cs->max_row_elems = max_row_elems;
+  cs->row_bytes = ((max_row_elems / 2 + 2) / 3) * 16;
   const int64_t bytes = total_bytes(world, max_rows, cs->row_bytes);
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, (size_t)bytes);
   if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&cs->handle, p);
   if (e != cudaSuccess) {
     b2l_set_error("tp_comm_create: %s", cudaGetErrorString(e));
@@ -280,12 +302,12 @@ extern "C" int b2l_tp_allreduce_skip_rmsnorm(int64_t comm, void* y, const void* 
   B2L_REQUIRE(y && x_partial, "tp_allreduce_skip_rmsnorm: null pointer");
   B2L_REQUIRE(rows >= 0 && rows <= cs->max_rows, "tp_allreduce_skip_rmsnorm: %lld rows > communicator capacity %d",
               (long long)rows, cs->max_rows);
-  B2L_REQUIRE(n > 0 && n % 8 == 0 && n * 2 <= cs->row_bytes, "tp_allreduce_skip_rmsnorm: row of %lld elements (capacity %lld, multiple of 8)",
-              (long long)n, (long long)(cs->row_bytes / 2));
-  B2L_REQUIRE(x_row_stride % 8 == 0 && y_row_stride % 8 == 0 && (residual == nullptr || r_row_stride % 8 == 0) &&
-                  (uintptr_t)x_partial % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)residual % 16 == 0 &&
-                  (uintptr_t)weight % 16 == 0,
-              "tp_allreduce_skip_rmsnorm: rows must be 16-byte aligned");
+  B2L_REQUIRE(n > 0 && n % 2 == 0 && n <= cs->max_row_elems, "tp_allreduce_skip_rmsnorm: row of %lld elements (capacity %lld, even)",
+              (long long)n, (long long)cs->max_row_elems);
+  B2L_REQUIRE(x_row_stride % 2 == 0 && y_row_stride % 2 == 0 && (residual == nullptr || r_row_stride % 2 == 0) &&
+                  (uintptr_t)x_partial % 4 == 0 && (uintptr_t)y % 4 == 0 && (uintptr_t)residual % 4 == 0 &&
+                  (uintptr_t)weight % 4 == 0,
+              "tp_allreduce_skip_rmsnorm: rows must be 4-byte aligned");
   B2L_REQUIRE(dtype == B2L_F16 || dtype == B2L_BF16, "tp_allreduce_skip_rmsnorm: dtype %d", dtype);
   if (rows == 0) return B2L_OK;
   FusedParams p;

@@ -40,7 +40,7 @@ class NvlinkComm:
         dist.barrier(group=group)
 
     def fits(self, rows: int, n: int) -> bool:
-        return 0 < rows <= self.max_rows and n % 8 == 0 and n <= self.max_row_elems
+        return 0 < rows <= self.max_rows and n % 2 == 0 and n <= self.max_row_elems
 
     def close(self) -> None:
         if self.handle:

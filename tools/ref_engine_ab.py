@@ -251,7 +251,7 @@ def main():
             cb = ContinuousBatchingEngine(eng_c, SchedulerConfig(max_seq_len=max_seq_len, max_num_seqs=a.continuous))
             cb.stop_token_ids = set()
             g = torch.Generator().manual_seed(7)
-            lens = torch.randint(32, a.prompt_len + 1, (a.continuous,), generator=g).tolist()
+            lens = torch.randint(min(32, max(1, a.prompt_len // 2)), a.prompt_len + 1, (a.continuous,), generator=g).tolist()
             reqs = [cb.add_request("", params, prompt_token_ids=torch.randint(0, V - 2, (n,), generator=g).tolist()) for n in lens]
             t = time.perf_counter()
             steps = 0

@@ -88,7 +88,8 @@ def main():
                 y1, r1o = allreduce_skip_rmsnorm(part.clone(), r1, w, 1e-5)
                 y2, r2o = K.skip_rmsnorm(truth32.to(torch.float16), r2, w, 1e-5)
                 assert torch.equal(r1o, r2o), "fused residual differs"
-                assert torch.equal(y1, y2), "fused norm output differs"
+                # the row's sum of squares is accumulated in a different order than the stand-alone norm: 1 ulp
+                torch.testing.assert_close(y1.float(), y2.float(), rtol=2e-3, atol=2e-3)
                 worst_fused = max(worst_fused, float((y1.float() - y2.float()).abs().max()))
         out.update(allreduce_vs_fp32_sum_max_abs=worst_sum, nccl_vs_fp32_sum_max_abs=worst_nccl, fused_vs_unfused_max_abs=worst_fused)
 
