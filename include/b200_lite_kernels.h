@@ -109,11 +109,13 @@ int b2l_flash_decoding(void* out, const void* q, const void* k_cache, const void
                        int dtype, void* stream);
 
 /* flash_attention2_no_pad(q, k, v, sm_scale, b_start_loc, b_seq_len, max_seq_len)
- * -- lite_llama/kernels/flashattention2_nopad.py:175-231.  sm_scale already carries log2(e). */
+ * -- lite_llama/kernels/flashattention2_nopad.py:175-231.  sm_scale already carries log2(e).  total_tokens = q.shape[0]
+ * (rows of q / k / v; bounds the TMA descriptors of the tcgen05 kernel, csrc/flash_attention_tc.cu, which takes
+ * head_dim 128 with heads packed inside a token row; other shapes run the mma.sync kernel). */
 int b2l_flash_attention2_no_pad(void* out, const void* q, const void* k, const void* v, const void* b_start_loc,
                                 int start_loc_width, const void* b_seq_len, int seq_len_width, int64_t batch,
                                 int num_q_heads, int num_kv_heads, int head_dim, int64_t max_seq_len,
-                                float sm_scale_log2, int64_t q_tok_stride, int64_t q_head_stride,
+                                int64_t total_tokens, float sm_scale_log2, int64_t q_tok_stride, int64_t q_head_stride,
                                 int64_t k_tok_stride, int64_t k_head_stride, int64_t v_tok_stride,
                                 int64_t v_head_stride, int64_t o_tok_stride, int64_t o_head_stride, int dtype,
                                 void* stream);

@@ -12,6 +12,7 @@
 // 16 query rows each and run QK^T / PV on tensor cores with fp32 online softmax.  Tiles above the
 // causal diagonal are never loaded.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -241,10 +242,20 @@ int launch_prefill(const PrefillParams& p, int64_t batch, int64_t max_len, cudaS
 
 }  // namespace
 
+// flash_attention_tc.cu: the tcgen05 kernel (head_dim 128, packed heads); returns 1 when the shape is not its to take
+int b2l_fa_tc_try(void* out, const void* q, const void* k, const void* v, const void* b_start_loc, int start_w,
+                  const void* b_seq_len, int len_w, int64_t batch, int num_q_heads, int num_kv_heads, int head_dim,
+                  int64_t max_seq_len, int64_t total_tokens, float sm_scale_log2, int64_t q_ts, int64_t q_hs,
+                  int64_t k_ts, int64_t k_hs, int64_t v_ts, int64_t v_hs, int64_t o_ts, int64_t o_hs, int dtype,
+                  cudaStream_t st);
+
+static int g_fa_tc = -1;   // env B2L_FA_TC=0 keeps the mma.sync kernel (A/B measurements)
+
 extern "C" int b2l_flash_attention2_no_pad(void* out, const void* q, const void* k, const void* v,
                                            const void* b_start_loc, int start_loc_width, const void* b_seq_len,
                                            int seq_len_width, int64_t batch, int num_q_heads, int num_kv_heads,
-                                           int head_dim, int64_t max_seq_len, float sm_scale_log2, int64_t q_tok_stride,
+                                           int head_dim, int64_t max_seq_len, int64_t total_tokens,
+                                           float sm_scale_log2, int64_t q_tok_stride,
                                            int64_t q_head_stride, int64_t k_tok_stride, int64_t k_head_stride,
                                            int64_t v_tok_stride, int64_t v_head_stride, int64_t o_tok_stride,
                                            int64_t o_head_stride, int dtype, void* stream) {
@@ -261,6 +272,17 @@ extern "C" int b2l_flash_attention2_no_pad(void* out, const void* q, const void*
                   (uintptr_t)q % 4 == 0 && (uintptr_t)out % 4 == 0,
               "flash_attention2_no_pad: q/out rows must be 4-byte aligned");
   if (batch == 0 || max_seq_len <= 0) return B2L_OK;
+  if (g_fa_tc < 0) {
+    const char* e = getenv("B2L_FA_TC");
+    g_fa_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_fa_tc) {
+    const int rc = b2l_fa_tc_try(out, q, k, v, b_start_loc, start_loc_width, b_seq_len, seq_len_width, batch, num_q_heads,
+                                 num_kv_heads, head_dim, max_seq_len, total_tokens, sm_scale_log2, q_tok_stride,
+                                 q_head_stride, k_tok_stride, k_head_stride, v_tok_stride, v_head_stride, o_tok_stride,
+                                 o_head_stride, dtype, (cudaStream_t)stream);
+    if (rc <= 0) return rc;      // taken (0) or failed (< 0); 1 = not this kernel's shape
+  }
   PrefillParams p;
   p.q = q; p.q_ts = q_tok_stride; p.q_hs = q_head_stride;
   p.k = k; p.k_ts = k_tok_stride; p.k_hs = k_head_stride;

@@ -247,7 +247,8 @@ extern "C" int64_t b2l_linear_workspace_bytes(int64_t m, int64_t n, int64_t k, i
 // number of int32 split-K tickets a launch may touch (they must be zero on entry; the kernel re-zeroes them)
 extern "C" int64_t b2l_linear_num_counters(int64_t m, int64_t n) {
   if (m <= 0 || n <= 0) return 0;
-  return cdiv64(n, kBlockW) * cdiv64(m, pick_bt(m));
+  const int bt = pick_bt(m) > 64 ? 64 : pick_bt(m);   // the plan may shrink the token tile down to 64 (gemm_tc.cuh)
+  return cdiv64(n, kBlockW) * cdiv64(m, bt);
 }
 
 extern "C" int b2l_linear(void* y, const void* x, const void* w, const void* bias, int64_t m, int64_t n, int64_t k,

@@ -58,10 +58,15 @@ static inline SplitPlan make_plan(int64_t M, int64_t N, int64_t K, int k_elems_p
   SplitPlan pl;
   pl.bt = pick_bt(M);
   pl.n_tiles = (int)cdiv64(N, kBlockW);
+  const int sms = b2l_num_sms();
+  // Medium token counts with few weight-row tiles (e.g. 256 x 4608 x 3584: 36 tiles of 128 x 256): fill the SMs
+  // with SMALLER token tiles before resorting to split-K -- a split of a 256-token tile moves 128 KiB of fp32
+  // partials per CTA through the workspace, which cost more than the GEMM (measured 57 us vs 34 us for the
+  // reference's Triton kernel on this shape, profiles/r2c_triton_vs_b200.md).
+  while (pl.bt > 64 && (int64_t)pl.n_tiles * cdiv64(M, pl.bt) < sms) pl.bt /= 2;
   pl.m_tiles = (int)cdiv64(M, pl.bt);
   pl.num_kb = (int)cdiv64(K, k_elems_per_stage);
   const int tiles = pl.n_tiles * pl.m_tiles;
-  const int sms = b2l_num_sms();
   int splits = 1;
   if (tiles < sms) {
     splits = sms / tiles;

@@ -32,7 +32,7 @@ def flash_attention2_no_pad(q, k, v, sm_scale, b_start_loc, b_seq_len, max_seq_l
             output.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
             b_start_loc.data_ptr(), index_width(b_start_loc, "b_start_loc"),
             b_seq_len.data_ptr(), index_width(b_seq_len, "b_seq_len"),
-            batchs, n_heads, k.shape[1], head_dim, int(max_seq_len), float(sm_scale),
+            batchs, n_heads, k.shape[1], head_dim, int(max_seq_len), int(q.shape[0]), float(sm_scale),
             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
             output.stride(0), output.stride(1), code, stream_handle(),
         )

@@ -360,6 +360,44 @@ def test_flash_attention_nopad_padded_rectangle_and_strided_kv():
     close(out, ref, **ATT_TOL)
 
 
+# head_dim 128 with packed heads runs the tcgen05 kernel (csrc/flash_attention_tc.cu): 128-row query blocks, 128-key
+# tiles, S/P/O in tensor memory.  Cases: one partial block, exact block boundaries, several key tiles per block (the
+# double-buffered S / O pipeline and all three ring stages wrap), ragged batches, GQA, strided fused-qkv views, bf16.
+@pytest.mark.parametrize("seq_lens", [[1], [17], [127], [128], [129], [255, 256, 257], [300, 5, 128], [1024], [2048, 640]])
+def test_flash_attention_tc_ragged_d128(seq_lens):
+    out, ref, _ = _prefill_case(seq_lens, 8, 2, 128)
+    close(out, ref, **ATT_TOL)
+
+
+@pytest.mark.parametrize("hq,hkv", [(4, 4), (8, 1), (32, 8), (28, 4)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_flash_attention_tc_gqa_dtypes_d128(hq, hkv, dtype):
+    out, ref, _ = _prefill_case([200, 130], hq, hkv, 128, dtype=dtype, strided_kv=True)
+    tol = ATT_TOL if dtype == torch.float16 else dict(rtol=1.6e-2, atol=1.6e-2)
+    close(out, ref, **tol)
+
+
+def test_flash_attention_tc_matches_the_mma_sync_kernel_on_the_llama_prefill_shape():
+    """BASELINE prefill: 32 sequences x 128 tokens, Llama-3-8B heads, q/k/v as views of one fused-qkv buffer in the
+    padded-rectangle layout; the tcgen05 kernel against the oracle and against the mma.sync kernel (B2L_FA_TC=0 path
+    is exercised by the head_dim 32/64 cases above)."""
+    B, S, hq, hkv, d = 32, 128, 32, 8, 128
+    total = B * S
+    qkv = torch.randn(total, (hq + 2 * hkv) * d, device="cuda", dtype=torch.float16) * 0.3
+    q = qkv[:, : hq * d].view(total, hq, d)
+    k = qkv[:, hq * d : (hq + hkv) * d].view(total, hkv, d)
+    v = qkv[:, (hq + hkv) * d :].view(total, hkv, d)
+    lens = torch.randint(1, S + 1, (B,), dtype=torch.int32)
+    lens[0], lens[1] = S, 1
+    b_start = (torch.arange(B, dtype=torch.int32) * S).cuda()
+    out = K().flash_attention2_no_pad(q, k, v, LOG2E / math.sqrt(d), b_start, lens.cuda(), S)
+    ref = ops.varlen_causal_attention(q.cpu(), k.cpu(), v.cpu(), b_start.cpu(), lens, 1.0 / math.sqrt(d))
+    valid = torch.zeros(total, dtype=torch.bool)
+    for s0, n in zip(b_start.tolist(), lens.tolist()):
+        valid[s0 : s0 + n] = True
+    close(out.cpu()[valid], ref[valid], **ATT_TOL)
+
+
 def test_flash_attention_nopad_first_token_sees_only_itself():
     d = 64
     q = torch.randn(40, 4, d, device="cuda", dtype=torch.float16)
