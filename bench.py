@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="llama-3-8b")
     ap.add_argument("--quant", default="int4", choices=["fp16", "int4", "int8", "fp8", "smoothquant"])
+    ap.add_argument("--max-seq-len", type=int, default=None, help="KV slot length per request (default: fits the run)")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--layers", type=int, default=None, help="override the layer count (debugging only)")
@@ -62,7 +63,8 @@ def workload_config(args, world):
     return {
         "workload": f"{args.model} {'W4A16 g128' if args.quant == 'int4' else args.quant} greedy decode, "
                     f"batch {args.batch}{'' if tp else '/GPU'}, prompt {args.prompt_len} -> {args.steps} new tokens "
-                    f"(BASELINE.json configs[2]; the metric's named config)",
+                    + ("(BASELINE.json configs[2]; the metric's named config)"
+                       if (args.model, args.quant) == ("llama-3-8b", "int4") else "(a BASELINE.json side configuration)"),
         "model": args.model, "quant": args.quant, "per_gpu_batch": args.batch,
         "global_batch": args.batch if tp else args.batch * world,
         "prompt_len": args.prompt_len, "parallelism": (f"tp{world}" if tp else f"dp{world}") if world > 1 else "single",
@@ -256,7 +258,7 @@ def kernel_breakdown(runner, batch: int, ctx: int, hbm_peak: float) -> list[dict
     L = len(dec.w.layers)
     x_h = torch.randn(batch, cfg.hidden_size, device=dev, dtype=torch.float16)
     x_q = torch.randn(batch, dec.q_size, device=dev, dtype=torch.float16)
-    x_i = torch.randn(batch, dec.inter, device=dev, dtype=torch.float16)
+    x_i = torch.randn(batch, max(dec.inter, 8), device=dev, dtype=torch.float16)
     out = []
 
     def add(name, fn, bytes_per_launch, launches):
@@ -270,8 +272,14 @@ def kernel_breakdown(runner, batch: int, ctx: int, hbm_peak: float) -> list[dict
     lw0 = dec.w.layers[0]
     add("qkv_proj", lambda: [apply_linear(x_h, lw.qkv) for lw in dec.w.layers], lw0.qkv.nbytes(), L)
     add("o_proj", lambda: [apply_linear(x_q, lw.o) for lw in dec.w.layers], lw0.o.nbytes(), L)
-    add("gate_up_proj", lambda: [apply_linear(x_h, lw.gate_up) for lw in dec.w.layers], lw0.gate_up.nbytes(), L)
-    add("down_proj", lambda: [apply_linear(x_i, lw.down) for lw in dec.w.layers], lw0.down.nbytes(), L)
+    if lw0.moe is None:
+        add("gate_up_proj", lambda: [apply_linear(x_h, lw.gate_up) for lw in dec.w.layers], lw0.gate_up.nbytes(), L)
+        add("down_proj", lambda: [apply_linear(x_i, lw.down) for lw in dec.w.layers], lw0.down.nbytes(), L)
+    else:
+        m0 = lw0.moe
+        touched = m0.w1.shape[0] * (1.0 - (1.0 - m0.top_k / m0.w1.shape[0]) ** batch)
+        add("moe_block(router+fused_moe)", lambda: [dec._moe(x_h, lw.moe) for lw in dec.w.layers],
+            touched * dec.w.moe_expert_bytes() + m0.router.numel() * 2, L)
     add("lm_head", lambda: K.linear(x_h, dec.w.lm_head), dec.w.lm_head.numel() * 2, 1)
     # flash decoding over every layer's pool at the mean timed context
     info = runner.atten_info
@@ -374,8 +382,12 @@ def main() -> None:
     e.record()
     torch.cuda.synchronize()
     prefill_ms = s.elapsed_time(e)
-    params_active = sum(lw.qkv.out_features * lw.qkv.in_features + lw.o.out_features * lw.o.in_features +
-                        lw.gate_up.out_features * lw.gate_up.in_features + lw.down.out_features * lw.down.in_features
+    def _ffn_params(lw):
+        if lw.moe is not None:      # active experts only
+            return lw.moe.top_k * (lw.moe.w1.shape[1] * lw.moe.w1.shape[2] + lw.moe.w2.shape[1] * lw.moe.w2.shape[2])
+        return lw.gate_up.out_features * lw.gate_up.in_features + lw.down.out_features * lw.down.in_features
+
+    params_active = sum(lw.qkv.out_features * lw.qkv.in_features + lw.o.out_features * lw.o.in_features + _ffn_params(lw)
                         for lw in runner.model.w.layers)
     prefill_flops = 2.0 * B * P * params_active + 2.0 * B * cfg.vocab_size * cfg.hidden_size \
         + 4.0 * B * cfg.num_heads * P * P * cfg.head_dim / 2 * cfg.num_layers
@@ -483,10 +495,16 @@ def main() -> None:
     mean_ctx = P + W + (K + 1) / 2
     kv_bytes_step = B * mean_ctx * 2 * runner.num_kv_heads * cfg.head_dim * 2 * cfg.num_layers
     step_bytes = weight_bytes + kv_bytes_step
+    if cfg.num_experts > 0:
+        # routed experts: expected number of DISTINCT experts a batch of B tokens touches per layer
+        touched = cfg.num_experts * (1.0 - (1.0 - cfg.num_experts_per_tok / cfg.num_experts) ** B)
+        step_bytes += touched * runner.model.w.moe_expert_bytes() * cfg.num_layers
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
-        "dtype": "f16 activations, int4 weights (fp32 accumulate)" if args.quant == "int4" else "f16",
+        "dtype": {"int4": "f16 activations, int4 weights (fp32 accumulate)", "fp16": "f16",
+                  "fp8": "f16 activations, fp8-e4m3 weights (fp32 accumulate)", "int8": "f16 activations, int8 weights",
+                  "smoothquant": "int8 activations x int8 weights (int32 accumulate), f16 elsewhere"}[args.quant],
         "data": "synthetic (random-init weights of the named shapes, random token ids)",
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 8,

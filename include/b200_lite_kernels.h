@@ -120,6 +120,16 @@ int b2l_flash_attention2_no_pad(void* out, const void* q, const void* k, const v
                                 int64_t v_head_stride, int64_t o_tok_stride, int64_t o_head_stride, int dtype,
                                 void* stream);
 
+/* rope_emb_forward + torch.cat + update_kv_buffer in ONE launch (lite_llama/kernels/rope_emb.py:86-134,
+ * lite_llama/models/base.py:76-79, lite_llama/kernels/update_kv_buffer.py:55-89): rotates q [T, n_qh, D] and
+ * k [T, n_kh, D] in place (same arithmetic as b2l_rope_emb), stores the rotated k rows and the v rows [T, n_kh, D] into
+ * kv_buffer [max_tokens, 2 * n_kh, D] at rows select_index[t] (K heads first).  Strides in elements. */
+int b2l_rope_kv_write(void* q, void* k, const void* v, const void* cos, const void* sin, const void* select_index,
+                      int index_width, void* kv_buffer, int64_t batch, int64_t seq_len, int n_qh, int n_kh,
+                      int head_dim, int64_t q_tok_stride, int64_t q_head_stride, int64_t k_tok_stride,
+                      int64_t k_head_stride, int64_t v_tok_stride, int64_t v_head_stride, int64_t cs_batch_stride,
+                      int64_t cs_seq_stride, int64_t d_tok_stride, int64_t d_head_stride, int dtype, void* stream);
+
 /* Dense projection y = x @ w.T (+ bias): the reference's F.linear call sites
  * (lite_llama/models/quantization/methods/unquantized.py:21-22, lite_llama/models/base.py:489). */
 int64_t b2l_linear_workspace_bytes(int64_t m, int64_t n, int64_t k, int elem_bytes);

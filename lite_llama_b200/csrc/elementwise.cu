@@ -335,6 +335,93 @@ extern "C" int b2l_rope_emb(void* q, void* k, const void* cos, const void* sin, 
 }
 
 // --------------------------------------------------------------------------- //
+// rope + KV-cache write in one launch: the reference rotates q and k (rope_emb.py:86-134), then
+// concatenates k|v and scatters the rows into the pool (models/base.py:76-79, update_kv_buffer.py:55-89) -- three
+// launches and two copies per layer.  Here one CTA per token rotates q in place, rotates k in place AND stores the
+// rotated row into the pool, and copies v into the pool.  Same arithmetic as rope_kernel (bit-identical results).
+// --------------------------------------------------------------------------- //
+template <typename T>
+__global__ void rope_kv_write_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v,
+                                     const T* __restrict__ cosp, const T* __restrict__ sinp,
+                                     const void* __restrict__ select_index, int idx_width, T* __restrict__ pool,
+                                     int seq_len, int n_qh, int n_kh, int hd, int64_t q_ts, int64_t q_hs, int64_t k_ts,
+                                     int64_t k_hs, int64_t v_ts, int64_t v_hs, int64_t cs_b, int64_t cs_s, int64_t d_ts,
+                                     int64_t d_hs) {
+  pdl_prologue();
+  using T2 = typename Vec2<T>::type;
+  const int64_t tok = blockIdx.x;
+  const int64_t b = tok / seq_len, s = tok % seq_len;
+  const T* cr = cosp + b * cs_b + s * cs_s;
+  const T* sr = sinp + b * cs_b + s * cs_s;
+  const int64_t dest = load_index(select_index, tok, idx_width);
+  const int half = hd / 2;
+  const int pairs = half / 2;                       // half2 units per half-row
+  const int rot = (n_qh + n_kh) * pairs;
+  const int vcopy = n_kh * half;                    // half2 units of the token's V heads
+  for (int i = threadIdx.x; i < rot + vcopy; i += blockDim.x) {
+    if (i < rot) {
+      const int h = i / pairs, p = i % pairs;
+      const bool is_k = h >= n_qh;
+      T* base = is_k ? k + tok * k_ts + (int64_t)(h - n_qh) * k_hs : q + tok * q_ts + (int64_t)h * q_hs;
+      T2* p1 = reinterpret_cast<T2*>(base) + p;
+      T2* p2 = reinterpret_cast<T2*>(base + half) + p;
+      T2 a = *p1, bb = *p2;
+      rope_pair(a, bb, reinterpret_cast<const T2*>(cr)[p], reinterpret_cast<const T2*>(sr)[p]);
+      *p1 = a;
+      *p2 = bb;
+      if (is_k) {
+        T* drow = pool + dest * d_ts + (int64_t)(h - n_qh) * d_hs;
+        reinterpret_cast<T2*>(drow)[p] = a;
+        reinterpret_cast<T2*>(drow + half)[p] = bb;
+      }
+    } else {
+      const int j = i - rot;
+      const int h = j / half, c = j % half;
+      const T2 val = reinterpret_cast<const T2*>(v + tok * v_ts + (int64_t)h * v_hs)[c];
+      reinterpret_cast<T2*>(pool + dest * d_ts + (int64_t)(n_kh + h) * d_hs)[c] = val;
+    }
+  }
+}
+
+extern "C" int b2l_rope_kv_write(void* q, void* k, const void* v, const void* cos, const void* sin,
+                                 const void* select_index, int index_width, void* kv_buffer, int64_t batch,
+                                 int64_t seq_len, int n_qh, int n_kh, int head_dim, int64_t q_tok_stride,
+                                 int64_t q_head_stride, int64_t k_tok_stride, int64_t k_head_stride,
+                                 int64_t v_tok_stride, int64_t v_head_stride, int64_t cs_batch_stride,
+                                 int64_t cs_seq_stride, int64_t d_tok_stride, int64_t d_head_stride, int dtype,
+                                 void* stream) {
+  B2L_REQUIRE(q && k && v && cos && sin && select_index && kv_buffer, "rope_kv_write: null pointer");
+  B2L_REQUIRE(batch >= 0 && seq_len >= 0 && n_qh > 0 && n_kh > 0 && head_dim >= 4 && head_dim % 4 == 0,
+              "rope_kv_write: bad shape (head_dim must be a multiple of 4)");
+  B2L_REQUIRE(index_width == 4 || index_width == 8, "rope_kv_write: index width %d", index_width);
+  const int64_t strides[] = {q_tok_stride, q_head_stride, k_tok_stride, k_head_stride, v_tok_stride, v_head_stride,
+                             cs_batch_stride, cs_seq_stride, d_tok_stride, d_head_stride};
+  for (int64_t st : strides) B2L_REQUIRE(st % 2 == 0, "rope_kv_write: strides must be even (4-byte accesses)");
+  B2L_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)cos | (uintptr_t)sin | (uintptr_t)kv_buffer) % 4 == 0,
+              "rope_kv_write: pointers must be 4-byte aligned");
+  const int64_t tokens = batch * seq_len;
+  if (tokens == 0) return B2L_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int work = (n_qh + n_kh) * (head_dim / 4) + n_kh * (head_dim / 2);
+  const int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
+  if (dtype == B2L_F16)
+    b2l_launch(rope_kv_write_kernel<__half>, dim3((unsigned)tokens), dim3(threads), (size_t)0, st, (__half*)q, (__half*)k,
+               (const __half*)v, (const __half*)cos, (const __half*)sin, select_index, index_width, (__half*)kv_buffer,
+               (int)seq_len, n_qh, n_kh, head_dim, q_tok_stride, q_head_stride, k_tok_stride, k_head_stride, v_tok_stride,
+               v_head_stride, cs_batch_stride, cs_seq_stride, d_tok_stride, d_head_stride);
+  else if (dtype == B2L_BF16)
+    b2l_launch(rope_kv_write_kernel<__nv_bfloat16>, dim3((unsigned)tokens), dim3(threads), (size_t)0, st,
+               (__nv_bfloat16*)q, (__nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)cos,
+               (const __nv_bfloat16*)sin, select_index, index_width, (__nv_bfloat16*)kv_buffer, (int)seq_len, n_qh, n_kh,
+               head_dim, q_tok_stride, q_head_stride, k_tok_stride, k_head_stride, v_tok_stride, v_head_stride,
+               cs_batch_stride, cs_seq_stride, d_tok_stride, d_head_stride);
+  else
+    B2L_UNSUPPORTED("rope_kv_write: dtype %d", dtype);
+  B2L_LAUNCH_CHECK();
+  return B2L_OK;
+}
+
+// --------------------------------------------------------------------------- //
 // swiglu_forward (reference: lite_llama/kernels/swiglu.py:24-65)
 //   c = (a_f32 * sigmoid(a_f32)) * b   -> activation dtype
 // Also covers fused_moe's _silu_and_mul_kernel (fused_moe.py:296-313) through

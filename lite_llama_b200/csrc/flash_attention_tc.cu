@@ -307,6 +307,158 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Prompts of at most 128 tokens (the BASELINE prefill shape: 32 x 128): every (sequence, head) is ONE 128 x 128 tile,
+// so the multi-tile pipeline above is all set-up.  This variant keeps the whole score row in registers (one TMEM read,
+// no running output), needs 96 KiB of shared memory and 256 TMEM columns, and is compiled for two resident CTAs per
+// SM: the loads of one CTA overlap the tensor-core and softmax work of the other.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSmemOneTile = 1024 + 1024 + 3 * kTileBytes;
+
+struct __align__(8) Ctl1 {
+  uint64_t qk_full, v_full, s_full, p_full, o_full;
+  uint32_t tmem_base;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+fa_tc_one_tile_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Ctl1* ctl = reinterpret_cast<Ctl1*>(smem);
+  uint8_t* q_s = smem + 1024;
+  uint8_t* k_s = q_s + kTileBytes;
+  uint8_t* v_s = k_s + kTileBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int kvh = head / p.G;
+  pdl_wait_prior();
+  const int64_t seq_len = load_index(p.seq_len, b, p.len_w);
+  if (seq_len <= 0) return;
+  const int64_t seq_start = load_index(p.start_loc, b, p.start_w);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(&ctl->qk_full, 1); mbar_init(&ctl->v_full, 1); mbar_init(&ctl->s_full, 1);
+    mbar_init(&ctl->p_full, 4); mbar_init(&ctl->o_full, 1);
+    mbar_fence_init();
+    // the loads do not need the tensor memory: issue them before the set-up barrier
+    const int tok = (int)seq_start;
+    mbar_arrive_expect_tx(&ctl->qk_full, 2 * kTileBytes);
+    tma_load_2d(q_s, &tmap_q, head * kD, tok, &ctl->qk_full);
+    tma_load_2d(q_s + kHalfBytes, &tmap_q, head * kD + 64, tok, &ctl->qk_full);
+    tma_load_2d(k_s, &tmap_k, kvh * kD, tok, &ctl->qk_full);
+    tma_load_2d(k_s + kHalfBytes, &tmap_k, kvh * kD + 64, tok, &ctl->qk_full);
+    mbar_arrive_expect_tx(&ctl->v_full, kTileBytes);
+    tma_load_2d(v_s, &tmap_v, kvh * kD, tok, &ctl->v_full);
+    tma_load_2d(v_s + kHalfBytes, &tmap_v, kvh * kD + 64, tok, &ctl->v_full);
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, 256);
+    tmem_relinquish();
+    pdl_launch_dependents();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 1) {
+    constexpr bool bf = std::is_same<T, __nv_bfloat16>::value;
+    constexpr uint32_t idesc_s = umma_idesc(1u, bf ? 1u : 0u, bf ? 1u : 0u, 0u, 0u, kBM, kBN);
+    constexpr uint32_t idesc_o = umma_idesc(1u, bf ? 1u : 0u, bf ? 1u : 0u, 0u, 1u, kBM, kD);
+    mbar_wait(&ctl->qk_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t q_desc = umma_desc_sw128_kmajor(smem_u32(q_s));
+      const uint64_t k_desc = umma_desc_sw128_kmajor(smem_u32(k_s));
+#pragma unroll
+      for (int kk = 0; kk < kD / 16; ++kk) {
+        const uint64_t off = (uint64_t)(((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4);
+        umma_f16(tmem_base, q_desc + off, k_desc + off, idesc_s, kk ? 1u : 0u);
+      }
+      tc_commit(&ctl->s_full);
+    }
+    __syncwarp();
+    mbar_wait(&ctl->p_full, 0);
+    mbar_wait(&ctl->v_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t v_addr = smem_u32(v_s);
+#pragma unroll
+      for (int kk = 0; kk < kBN / 16; ++kk) {
+        const uint64_t v_desc = umma_desc_sw128_mnmajor(v_addr + kk * 2048, kHalfBytes, 1024);
+        umma_ts(tmem_base + 128u, tmem_base + kk * 8, v_desc, idesc_o, kk ? 1u : 0u);
+      }
+      tc_commit(&ctl->o_full);
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    mbar_wait(&ctl->s_full, 0);
+    tc_fence_after();
+    float s[kBN];
+#pragma unroll
+    for (int c = 0; c < kBN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(lane_base + c, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kBN; ++i) mx = i <= row ? fmaxf(mx, s[i]) : mx;      // causal: key i visible iff i <= row
+    const float base = mx * p.scale_log2;
+    float lsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kBN; c += 32) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = (c + i <= row) ? fast_exp2(fmaf(s[c + i], p.scale_log2, -base)) : 0.f;
+        const float p1 = (c + i + 1 <= row) ? fast_exp2(fmaf(s[c + i + 1], p.scale_log2, -base)) : 0.f;
+        lsum += p0 + p1;
+        pk[i >> 1] = pack2<T>(p0, p1);
+      }
+      tmem_st_32x32b_x16(lane_base + (c >> 1), pk);
+    }
+    tc_wait_st_();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->p_full);
+    const float inv = 1.0f / lsum;
+    mbar_wait(&ctl->o_full, 0);
+    tc_fence_after();
+    if (row < seq_len) {
+      T* orow = reinterpret_cast<T*>(p.out) + (seq_start + row) * p.o_ts + (int64_t)head * p.o_hs;
+#pragma unroll
+      for (int c = 0; c < kD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_base + 128u + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack2<T>(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          w.y = pack2<T>(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          w.z = pack2<T>(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          w.w = pack2<T>(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c + i) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 template <typename T>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int64_t batch,
                   int num_q_heads, int64_t max_len, cudaStream_t st) {
@@ -316,6 +468,17 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     B2L_CUDA_CHECK(cudaFuncSetAttribute(fa_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set[dev] = true;
+  }
+  if (max_len <= kBM) {
+    static bool attr1_set[64] = {false};
+    if (dev >= 0 && dev < 64 && !attr1_set[dev]) {
+      B2L_CUDA_CHECK(cudaFuncSetAttribute(fa_tc_one_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOneTile));
+      attr1_set[dev] = true;
+    }
+    dim3 grid1(1, (unsigned)num_q_heads, (unsigned)batch);
+    b2l_launch(fa_tc_one_tile_kernel<T>, dim3(grid1), dim3(kThreads), (size_t)kSmemOneTile, st, tq, tk, tv, p);
+    B2L_LAUNCH_CHECK();
+    return B2L_OK;
   }
   dim3 grid((unsigned)cdiv64(max_len, kBM), (unsigned)num_q_heads, (unsigned)batch);
   b2l_launch(fa_tc_kernel<T>, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, st, tq, tk, tv, p);

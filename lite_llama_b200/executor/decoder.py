@@ -24,17 +24,42 @@ from ..distributed import divide, get_tp_rank, get_tp_world_size
 from ..kernels import (
     flash_attention2_no_pad,
     flash_decoding,
+    fused_moe,
     linear,
+    route_topk,
     rope_emb_inplace,
+    rope_kv_write,
     skip_rmsnorm,
     swiglu_forward,
     update_kv_buffer,
 )
 from ..kernels.tp_fused import allreduce_skip_rmsnorm
 from ..quantization import LinearWeights, apply_linear, make_linear_weights
+from ..quantization.params import quantize_fp8_blockwise, reblock_scales
 from .model_config import ModelConfig
 
 _LOG2E = 1.4426950408889634
+
+
+@dataclass
+class MoeWeights:
+    """One routed-expert FFN (reference: Qwen3MoeSparseMoeBlock, lite_llama/models/qwen3_moe.py:48-122). Experts are
+    stacked; ``w1`` = gate rows then up rows of every expert. Under TP each rank keeps ``I / tp`` intermediate
+    columns of EVERY expert (models/weights.py:129-130); the router is replicated and never quantised."""
+
+    router: torch.Tensor                  # [E, hidden], activation dtype
+    w1: torch.Tensor                      # [E, 2 * I_local, hidden]  fp16 | uint8 (e4m3 bits)
+    w2: torch.Tensor                      # [E, hidden, I_local]
+    w1_scale: torch.Tensor | None = None  # fp32 [E, ceil(2 I_local / group_n), ceil(hidden / group_k)]
+    w2_scale: torch.Tensor | None = None  # fp32 [E, ceil(hidden / group_n), ceil(I_local / group_k)]
+    group_n: int = 0
+    group_k: int = 0
+    top_k: int = 8
+    norm_topk_prob: bool = True
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.router, self.w1, self.w2, self.w1_scale, self.w2_scale)
+                   if t is not None)
 
 
 @dataclass
@@ -43,10 +68,11 @@ class LayerWeights:
     post_norm: torch.Tensor
     qkv: LinearWeights
     o: LinearWeights
-    gate_up: LinearWeights
-    down: LinearWeights
+    gate_up: LinearWeights | None = None
+    down: LinearWeights | None = None
     q_norm: torch.Tensor | None = None
     k_norm: torch.Tensor | None = None
+    moe: MoeWeights | None = None
 
 
 @dataclass
@@ -60,9 +86,49 @@ class DecoderWeights:
         """Weight bytes one decode step must stream (embedding gather excluded)."""
         total = self.lm_head.numel() * self.lm_head.element_size()
         for lw in self.layers:
-            total += lw.qkv.nbytes() + lw.o.nbytes() + lw.gate_up.nbytes() + lw.down.nbytes()
+            total += lw.qkv.nbytes() + lw.o.nbytes()
+            if lw.moe is None:
+                total += lw.gate_up.nbytes() + lw.down.nbytes()
+            else:
+                total += lw.moe.router.numel() * lw.moe.router.element_size()   # experts: see moe_expert_bytes()
             total += (lw.input_norm.numel() + lw.post_norm.numel()) * 2
         return total
+
+    def moe_expert_bytes(self) -> int:
+        """Bytes of ONE expert (both matrices + scales) on this rank, summed over layers / num_layers."""
+        moe = [lw.moe for lw in self.layers if lw.moe is not None]
+        if not moe:
+            return 0
+        m = moe[0]
+        e = m.w1.shape[0]
+        return (m.nbytes() - m.router.numel() * m.router.element_size()) // e
+
+
+def make_moe_weights(cfg: ModelConfig, router, gate, up, down, method: str, tp: int, rank: int,
+                     dtype: torch.dtype) -> MoeWeights:
+    """Shard + store one layer's experts. ``gate``/``up`` ``[E, I, h]``, ``down`` ``[E, h, I]`` are the FULL matrices;
+    fp8 follows the checkpoint format: quantise in 128 x 128 blocks over the full tensors, then cut the shard out of
+    codes and scales. A shard boundary inside a 128-block (I / tp = 192 at TP = 4) is handled by refining the scale
+    grid to gcd(128, I / tp) first (``reblock_scales``), which the grouped GEMM takes as group_n / group_k."""
+    inter = cfg.moe_intermediate_size
+    il = divide(inter, tp, "MoE intermediate")
+    lo, hi = rank * il, (rank + 1) * il
+    kw = dict(top_k=cfg.num_experts_per_tok, norm_topk_prob=cfg.norm_topk_prob)
+    if method != "fp8":
+        w1 = torch.cat([gate[:, lo:hi], up[:, lo:hi]], dim=1).to(dtype).contiguous()
+        return MoeWeights(router.to(dtype), w1, down[:, :, lo:hi].to(dtype).contiguous(), **kw)
+    blk = 128
+    g = math.gcd(blk, il)
+    qg, sg = quantize_fp8_blockwise(gate, blk)
+    qu, su = quantize_fp8_blockwise(up, blk)
+    qd, sd = quantize_fp8_blockwise(down, blk)
+    if g != blk:        # refine every scale grid to g x g so that one (group_n, group_k) serves w1 and w2
+        sg, su, sd = (reblock_scales(reblock_scales(t, blk, g, 1), blk, g, 2) for t in (sg, su, sd))
+    w1 = torch.cat([qg[:, lo:hi], qu[:, lo:hi]], dim=1).contiguous()
+    w1s = torch.cat([sg[:, lo // g:hi // g], su[:, lo // g:hi // g]], dim=1).contiguous()
+    w2 = qd[:, :, lo:hi].contiguous()
+    w2s = sd[:, :, lo // g:hi // g].contiguous()
+    return MoeWeights(router.to(dtype), w1, w2, w1s, w2s, group_n=g, group_k=g, **kw)
 
 
 def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda", seed: int = 0,
@@ -74,7 +140,7 @@ def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda",
     (lite_llama/models/base.py:366,425-429)."""
     tp, rank = get_tp_world_size(), get_tp_rank()
     hq, hkv = divide(cfg.num_heads, tp, "attention heads"), divide(cfg.num_kv_heads, tp, "key/value heads")
-    inter = divide(cfg.intermediate_size, tp, "MLP intermediate")
+    inter = divide(cfg.intermediate_size, tp, "MLP intermediate") if cfg.num_experts == 0 else 0
     d, h = cfg.head_dim, cfg.hidden_size
     draw_device = draw_device or device   # tests draw on the CPU to share weights with the oracle
     gen = torch.Generator(device=draw_device).manual_seed(seed)
@@ -89,8 +155,10 @@ def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda",
     for _ in range(cfg.num_layers):
         wq, wk, wv = draw(cfg.q_size, h), draw(cfg.kv_size, h), draw(cfg.kv_size, h)
         wo = draw(h, cfg.q_size)
-        wg, wu = draw(cfg.intermediate_size, h), draw(cfg.intermediate_size, h)
-        wd = draw(h, cfg.intermediate_size)
+        is_moe = cfg.num_experts > 0
+        if not is_moe:
+            wg, wu = draw(cfg.intermediate_size, h), draw(cfg.intermediate_size, h)
+            wd = draw(h, cfg.intermediate_size)
         bias = None
         if cfg.qkv_bias:
             bq, bk, bv = draw(cfg.q_size), draw(cfg.kv_size), draw(cfg.kv_size)
@@ -99,8 +167,9 @@ def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda",
         qkv = torch.cat([wq[rank * hq * d:(rank + 1) * hq * d], wk[rank * hkv * d:(rank + 1) * hkv * d],
                          wv[rank * hkv * d:(rank + 1) * hkv * d]], dim=0)
         o = wo[:, rank * hq * d:(rank + 1) * hq * d]
-        gu = torch.cat([wg[rank * inter:(rank + 1) * inter], wu[rank * inter:(rank + 1) * inter]], dim=0)
-        dn = wd[:, rank * inter:(rank + 1) * inter]
+        if not is_moe:
+            gu = torch.cat([wg[rank * inter:(rank + 1) * inter], wu[rank * inter:(rank + 1) * inter]], dim=0)
+            dn = wd[:, rank * inter:(rank + 1) * inter]
 
         def pack(w, b=None):
             w = w.contiguous()
@@ -108,13 +177,22 @@ def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda",
 
         lw = LayerWeights(
             input_norm=torch.ones(h, device=device, dtype=dtype), post_norm=torch.ones(h, device=device, dtype=dtype),
-            qkv=pack(qkv, bias), o=pack(o), gate_up=pack(gu), down=pack(dn),
+            qkv=pack(qkv, bias), o=pack(o),
         )
+        if is_moe:
+            e, im = cfg.num_experts, cfg.moe_intermediate_size
+            router = draw(e, h)
+            gate, up, down = draw(e, im, h), draw(e, im, h), draw(e, h, im)
+            lw.moe = make_moe_weights(cfg, router, gate, up, down, method, tp, rank, dtype)
+            del gate, up, down
+        else:
+            lw.gate_up, lw.down = pack(gu), pack(dn)
+            del wg, wu, wd, gu, dn
         if cfg.use_qk_norm:
             lw.q_norm = torch.ones(d, device=device, dtype=dtype)
             lw.k_norm = torch.ones(d, device=device, dtype=dtype)
         out.layers.append(lw)
-        del wq, wk, wv, wo, wg, wu, wd, qkv, o, gu, dn
+        del wq, wk, wv, wo, qkv, o
     return out
 
 
@@ -144,7 +222,7 @@ class Decoder:
         self.head_dim = cfg.head_dim
         self.q_size = self.num_heads * self.head_dim
         self.kv_size = self.num_kv_heads * self.head_dim
-        self.inter = divide(cfg.intermediate_size, tp, "MLP intermediate")
+        self.inter = divide(cfg.intermediate_size, tp, "MLP intermediate") if cfg.num_experts == 0 else 0
         self.scale = 1.0 / math.sqrt(cfg.head_dim)
         self.cos_table, self.sin_table = build_rope_table(cfg, max_pos, device, dtype)
 
@@ -167,13 +245,12 @@ class Decoder:
         if lw.q_norm is not None:                                                       # base.py:222-225
             xq, _ = skip_rmsnorm(xq, None, lw.q_norm, eps)
             xk, _ = skip_rmsnorm(xk, None, lw.k_norm, eps)
-        rope_emb_inplace(xq, xk, cos, sin, batch, seq_len)                              # base.py:228
         kv_buffer = atten_info.kv_buffer[li]
-        if lw.q_norm is None:
-            # k|v are adjacent column blocks of qkv: one strided [tokens, 2*Hkv, D] source, no cat
-            xkv = qkv[:, self.q_size :].view(tokens, 2 * self.num_kv_heads, self.head_dim)
-            update_kv_buffer(xkv, atten_info.cur_select_index, kv_buffer)              # base.py:76-79
+        if self.head_dim % 4 == 0:
+            # rope (base.py:228) + cat + cache write (base.py:76-79) in one launch; q/k rotate where they lie
+            rope_kv_write(xq, xk, xv, cos, sin, atten_info.cur_select_index, kv_buffer, batch, seq_len)
         else:
+            rope_emb_inplace(xq, xk, cos, sin, batch, seq_len)
             from ..kernels import update_kv_buffer_split
 
             update_kv_buffer_split(xk, xv, atten_info.cur_select_index, kv_buffer)
@@ -187,10 +264,23 @@ class Decoder:
         o = apply_linear(attn.view(tokens, self.q_size), lw.o)                          # base.py:245 (partial)
         # all-reduce (linear.py:160-161) + residual add + post-attention norm (base.py:312) in one kernel
         hidden, residual = allreduce_skip_rmsnorm(o.view(batch, seq_len, -1), residual, lw.post_norm, eps)
+        if lw.moe is not None:
+            down = self._moe(hidden.view(tokens, -1), lw.moe)                           # qwen3_moe.py:102-111 (partial)
+            return down.view(batch, seq_len, -1), residual
         gu = apply_linear(hidden.view(tokens, -1), lw.gate_up)                          # base.py:263-264
         act = swiglu_forward(gu[:, : self.inter], gu[:, self.inter :])
         down = apply_linear(act, lw.down)                                               # partial: reduced by the next norm
         return down.view(batch, seq_len, -1), residual
+
+    @staticmethod
+    def _moe(x: torch.Tensor, m: MoeWeights) -> torch.Tensor:
+        """Router (fp16 logits -> fp32 softmax -> top-k -> renormalise, qwen3_moe.py:85-100) + routed SwiGLU experts
+        (fused_moe). Under TP the result is this rank's partial sum over its slice of every expert's intermediate
+        dimension; its all-reduce (qwen3_moe.py:110) is fused into the next norm like the dense MLP's."""
+        logits = linear(x, m.router)
+        weights, ids = route_topk(logits, m.top_k, m.norm_topk_prob)
+        return fused_moe(x, m.w1, m.w2, weights, ids, w1_scale=m.w1_scale, w2_scale=m.w2_scale,
+                         group_n=m.group_n, group_k=m.group_k)
 
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, atten_info,

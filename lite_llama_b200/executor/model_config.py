@@ -25,6 +25,11 @@ class ModelConfig:
     use_qk_norm: bool = False
     tie_word_embeddings: bool = False
     max_seq_len: int = 2048
+    # routed-expert FFN (reference: lite_llama/models/qwen3_moe.py:48-122); 0 experts = dense SwiGLU MLP
+    num_experts: int = 0
+    num_experts_per_tok: int = 0
+    moe_intermediate_size: int = 0
+    norm_topk_prob: bool = True
 
     @property
     def q_size(self) -> int:
@@ -52,10 +57,14 @@ PRESETS: dict[str, ModelConfig] = {
                                 qkv_bias=True, tie_word_embeddings=True),
     "qwen3-8b": ModelConfig("qwen3-8b", 4096, 36, 32, 8, 128, 12288, 151936, rope_theta=1e6, rms_norm_eps=1e-6,
                             use_qk_norm=True),
+    "qwen3-30b-a3b": ModelConfig("qwen3-30b-a3b", 2048, 48, 32, 4, 128, 6144, 151936, rope_theta=1e6, rms_norm_eps=1e-6,
+                                 use_qk_norm=True, num_experts=128, num_experts_per_tok=8, moe_intermediate_size=768),
     # small geometries for tests (same code paths, seconds on CPU for the oracle)
     "tiny-llama": ModelConfig("tiny-llama", 256, 2, 8, 2, 32, 512, 1000, rope_theta=1e4),
     "tiny-qwen3": ModelConfig("tiny-qwen3", 256, 2, 8, 4, 32, 512, 1000, rope_theta=1e4, qkv_bias=False,
                               use_qk_norm=True, rms_norm_eps=1e-6),
+    "tiny-qwen3-moe": ModelConfig("tiny-qwen3-moe", 256, 2, 8, 4, 32, 512, 1000, rope_theta=1e4, use_qk_norm=True,
+                                  rms_norm_eps=1e-6, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128),
     "tiny-qwen2": ModelConfig("tiny-qwen2", 256, 2, 8, 2, 32, 512, 1000, rope_theta=1e4, qkv_bias=True,
                               rms_norm_eps=1e-6),
 }

@@ -9,7 +9,7 @@ from .flashattention2_nopad import flash_attention2_no_pad
 from .flashdecoding import flash_decoding
 from .fused_moe import fused_moe, moe_align_block_size, route_topk
 from .linear import linear
-from .rope_emb import rope_emb_forward, rope_emb_inplace
+from .rope_emb import rope_emb_forward, rope_emb_inplace, rope_kv_write
 from .skip_rmsnorm import skip_rmsnorm
 from .swiglu import swiglu_forward
 from .update_kv_buffer import update_kv_buffer, update_kv_buffer_split
@@ -25,6 +25,7 @@ __all__ = [
     "linear",
     "rope_emb_forward",
     "rope_emb_inplace",
+    "rope_kv_write",
     "skip_rmsnorm",
     "swiglu_forward",
     "update_kv_buffer",

@@ -111,8 +111,11 @@ def fused_moe(
     kind = _quant_kind(w1, w1_scale)
     if kind != _quant_kind(w2, w2_scale):
         raise ValueError("w1 and w2 must use the same quantisation format")
-    if kind and group_k % 128 != 0 and group_k < min(hidden, intermediate):
-        raise ValueError(f"group_k ({group_k}) must be a multiple of 128 unless it covers K")
+    # the reference asks for multiples of 128 (fused_moe.py:391-394); this kernel closes an accumulator segment every
+    # group_k elements and takes any multiple of 16, which is what sub-block tensor-parallel shards need (TP = 4 of
+    # Qwen3-30B-A3B: 192 columns per rank -> 64-wide scale groups)
+    if kind and group_k % 16 != 0 and group_k < min(hidden, intermediate):
+        raise ValueError(f"group_k ({group_k}) must be a multiple of 16 unless it covers K")
     if kind == _KIND_F16 and w1.dtype != dtype:
         raise ValueError("fp16 expert weights must match the activation dtype")
     x = hidden_states if hidden_states.stride(-1) == 1 and hidden_states.stride(0) % 8 == 0 else hidden_states.contiguous()

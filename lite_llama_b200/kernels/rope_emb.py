@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from ._common import check, dtype_code, lib, require_cuda, stream_handle
+from ._common import check, dtype_code, index_width, lib, require_cuda, stream_handle
 
 
 @torch.no_grad()
@@ -53,6 +53,30 @@ def rope_emb_inplace(q, k, cos, sin, batch_size, seq_len):
             q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(), batch_size, seq_len, n_qh, n_kh, hd,
             q.stride(0), q.stride(1), k.stride(0), k.stride(1), cos.stride(0), cos.stride(1),
             dtype_code(q, "q"), stream_handle(),
+        )
+    )
+    return q, k
+
+
+@torch.no_grad()
+def rope_kv_write(q, k, v, cos, sin, select_index, kv_buffer, batch_size, seq_len):
+    """RoPE on ``q``/``k`` (in place, where they lie) + the K|V cache write in one launch: what the reference does
+    with ``rope_emb_forward`` -> ``torch.cat([xk, xv])`` -> ``update_kv_buffer`` (models/base.py:76-79,228).
+    ``kv_buffer [max_tokens, 2*Hkv, D]`` receives the rotated ``k`` rows and the ``v`` rows at ``select_index``."""
+    require_cuda(q, k, v, cos, sin, select_index, kv_buffer)
+    n, n_qh, hd = q.shape
+    n_kh = k.shape[1]
+    assert batch_size * seq_len == n and v.shape[1] == n_kh and kv_buffer.shape[1] == 2 * n_kh
+    if any(t.stride(-1) != 1 for t in (q, k, v, cos, sin, kv_buffer)):
+        raise ValueError("rope_kv_write: innermost dimension must be contiguous")
+    if cos.dtype != q.dtype or sin.dtype != q.dtype or kv_buffer.dtype != q.dtype:
+        raise ValueError("rope_kv_write: cos/sin/kv_buffer must be in the activation dtype")
+    check(
+        lib().b2l_rope_kv_write(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), cos.data_ptr(), sin.data_ptr(), select_index.data_ptr(),
+            index_width(select_index, "select_index"), kv_buffer.data_ptr(), batch_size, seq_len, n_qh, n_kh, hd,
+            q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), cos.stride(0), cos.stride(1),
+            kv_buffer.stride(0), kv_buffer.stride(1), dtype_code(q, "q"), stream_handle(),
         )
     )
     return q, k

@@ -59,3 +59,31 @@ def quantize_fp8_per_channel(weight: torch.Tensor):
     scale = torch.where(scale > 0, scale, torch.ones_like(scale))
     q = (weight.float() / scale).clamp_(-FP8_E4M3_MAX, FP8_E4M3_MAX).to(torch.float8_e4m3fn)
     return q.view(torch.uint8), scale
+
+
+def quantize_fp8_blockwise(weight: torch.Tensor, block: int = 128):
+    """``[..., N, K]`` float -> (uint8 e4m3 bit patterns, fp32 scales ``[..., ceil(N/block), ceil(K/block)]``) with one
+    scale per ``block x block`` tile = tile absmax / 448: the fine-grained FP8 format of the Qwen3 / DeepSeek
+    checkpoints (lite_llama/models/quantization/config.py:33, executor/weight_utils.py:59-72 dequantises
+    ``code * scale`` per tile)."""
+    *lead, n, k = weight.shape
+    nb, kb = (n + block - 1) // block, (k + block - 1) // block
+    w = weight.float()
+    if nb * block != n or kb * block != k:
+        w = torch.nn.functional.pad(w, (0, kb * block - k, 0, nb * block - n))
+    tiles = w.reshape(*lead, nb, block, kb, block)
+    amax = tiles.abs().amax(dim=(-3, -1))
+    scales = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+    q = (tiles / scales[..., :, None, :, None]).reshape(*lead, nb * block, kb * block)[..., :n, :k]
+    return q.to(torch.float8_e4m3fn).view(torch.uint8).contiguous(), scales.contiguous()
+
+
+def reblock_scales(scales: torch.Tensor, block: int, new_block: int, dim: int) -> torch.Tensor:
+    """Refine block scales along ``dim`` from ``block`` to ``new_block`` elements per scale (``new_block`` divides
+    ``block``): every sub-block inherits its parent's scale, so ``code * scale`` is unchanged. This is what lets a
+    tensor-parallel shard start in the middle of a 128-wide checkpoint block (Qwen3-30B-A3B: 768 / 4 = 192 expert
+    columns per rank) -- the reference requires shards to hold whole scale blocks (models/linear.py:164-177) and
+    therefore loads this model at TP = 2 only."""
+    if block % new_block != 0:
+        raise ValueError(f"new block {new_block} must divide {block}")
+    return scales.repeat_interleave(block // new_block, dim=dim)

@@ -32,6 +32,7 @@ class CpuLayer:
     bkv: torch.Tensor | None = None
     q_norm: torch.Tensor | None = None
     k_norm: torch.Tensor | None = None
+    moe: dict | None = None   # routed-expert FFN instead of wgate/wup/wdown (lite_llama/models/qwen3_moe.py:48-122)
 
 
 def _maybe_quant(w: torch.Tensor, method: str, group_size: int = 128) -> torch.Tensor:
@@ -65,18 +66,37 @@ def random_cpu_layers(cfg, method: str, num_layers: int, seed: int = 0, draw=Non
     for _ in range(num_layers):
         wq, wk, wv = draw(cfg.q_size, h), draw(cfg.kv_size, h), draw(cfg.kv_size, h)
         wo = draw(h, cfg.q_size)
-        wg, wu = draw(cfg.intermediate_size, h), draw(cfg.intermediate_size, h)
-        wd = draw(h, cfg.intermediate_size)
+        is_moe = getattr(cfg, "num_experts", 0) > 0
+        if not is_moe:
+            wg, wu = draw(cfg.intermediate_size, h), draw(cfg.intermediate_size, h)
+            wd = draw(h, cfg.intermediate_size)
         bq = bkv = None
         if cfg.qkv_bias:
             bq_, bk_, bv_ = draw(cfg.q_size), draw(cfg.kv_size), draw(cfg.kv_size)
             bq, bkv = bq_.to(torch.float16).float(), torch.cat([bk_, bv_]).to(torch.float16).float()
         # the GPU side quantises the row-concatenated [q|k|v] and [gate|up] matrices; per-row /
         # per-(row, group) schemes make that identical to quantising each piece on its own
+        moe = None
+        if is_moe:
+            e, im = cfg.num_experts, cfg.moe_intermediate_size
+            router = draw(e, h).to(torch.float16)
+            gate, up, down = draw(e, im, h), draw(e, im, h), draw(e, h, im)
+            moe = dict(router=router, top_k=cfg.num_experts_per_tok, norm=cfg.norm_topk_prob, group_n=0, group_k=0,
+                       w1_scale=None, w2_scale=None)
+            if method == "fp8":    # checkpoint format: 128 x 128 block scales over the full expert matrices
+                qg, sg = ops.quantize_fp8_blockwise(gate)
+                qu, su = ops.quantize_fp8_blockwise(up)
+                qd, sd = ops.quantize_fp8_blockwise(down)
+                moe.update(w1=torch.cat([qg, qu], dim=1), w1_scale=torch.cat([sg, su], dim=1), w2=qd, w2_scale=sd,
+                           group_n=128, group_k=128)
+            else:
+                moe.update(w1=torch.cat([gate, up], dim=1).to(torch.float16), w2=down.to(torch.float16))
+            wg = wu = wd = None
         layers.append(CpuLayer(
             input_norm=torch.ones(h, dtype=torch.float16), post_norm=torch.ones(h, dtype=torch.float16),
             wq=_maybe_quant(wq, method), wkv=_maybe_quant(torch.cat([wk, wv]), method), wo=_maybe_quant(wo, method),
-            wgate=_maybe_quant(wg, method), wup=_maybe_quant(wu, method), wdown=_maybe_quant(wd, method),
+            wgate=None if is_moe else _maybe_quant(wg, method), wup=None if is_moe else _maybe_quant(wu, method),
+            wdown=None if is_moe else _maybe_quant(wd, method), moe=moe,
             bq=bq, bkv=bkv,
             q_norm=torch.ones(cfg.head_dim, dtype=torch.float16) if cfg.use_qk_norm else None,
             k_norm=torch.ones(cfg.head_dim, dtype=torch.float16) if cfg.use_qk_norm else None,
@@ -151,6 +171,12 @@ class CpuDecoder:
             o = self.lin(attn.reshape(T, cfg.q_size), L.wo)
             hidden, residual = ops.skip_rmsnorm(o.view(B, S, -1), residual, L.post_norm, cfg.rms_norm_eps)
             x2 = hidden.reshape(T, cfg.hidden_size)
+            if L.moe is not None:
+                m = L.moe
+                w, ids = ops.route_topk(x2, m["router"], m["top_k"], m["norm"])
+                hidden = ops.fused_moe(x2, m["w1"], m["w2"], w, ids, m["w1_scale"], m["w2_scale"], m["group_n"],
+                                       m["group_k"]).view(B, S, -1)
+                continue
             act = ops.swiglu(self.lin(x2, L.wgate), self.lin(x2, L.wup))
             hidden = self.lin(act, L.wdown).view(B, S, -1)
         hidden, _ = ops.skip_rmsnorm(hidden, residual, self.final_norm, cfg.rms_norm_eps)

@@ -217,6 +217,22 @@ def quantize_fp8_per_channel(weight):
     return q.view(torch.uint8), scale
 
 
+def quantize_fp8_blockwise(weight, block=128):
+    """Fine-grained FP8 checkpoint format (lite_llama/models/quantization/config.py:33 FP8_BLOCK = 128): one fp32
+    scale per ``block x block`` tile = tile absmax / 448, codes = round-to-nearest e4m3 of ``w / scale``;
+    dequantisation is ``code * scale`` per tile (lite_llama/executor/weight_utils.py:59-72)."""
+    *lead, n, k = weight.shape
+    nb, kb = (n + block - 1) // block, (k + block - 1) // block
+    w = weight.float()
+    if nb * block != n or kb * block != k:
+        w = F.pad(w, (0, kb * block - k, 0, nb * block - n))
+    tiles = w.reshape(*lead, nb, block, kb, block)
+    amax = tiles.abs().amax(dim=(-3, -1))
+    scales = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+    q = (tiles / scales[..., :, None, :, None]).reshape(*lead, nb * block, kb * block)[..., :n, :k]
+    return q.to(torch.float8_e4m3fn).view(torch.uint8).contiguous(), scales.contiguous()
+
+
 def fp8_e4m3_bits_to_float(q_u8):
     """The reference's bit trick (kernels/quantization/w8a16.py:49-62) followed by its x256
     (w8a16.py:120): ``((b&0x80)<<8)|((b&0x7F)<<7)`` viewed as fp16, times 256. Bit-exact for all

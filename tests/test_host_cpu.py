@@ -154,3 +154,55 @@ def test_stream_k_partition_arithmetic():
     for _ in range(300):
         nt, nrb = rng.randint(1, 300), rng.randint(1, 64)
         check(nt, nrb, max(1, min(nt * nrb // 2, 148)))
+
+
+def test_fp8_block_quantiser_and_sub_block_tensor_parallel_shards():
+    """Fine-grained FP8 (128 x 128 block scales, the Qwen3-30B-A3B-FP8 checkpoint format): the product's quantiser
+    equals the oracle's; refining the scale grid (reblock_scales) leaves every dequantised value unchanged; and a
+    tensor-parallel shard that starts inside a 128-block (768 / 4 = 192 columns per rank) dequantises to the same
+    values as the matching slice of the full matrix -- the case the reference refuses to load
+    (lite_llama/models/linear.py:164-177)."""
+    from lite_llama_b200.quantization.params import quantize_fp8_blockwise, reblock_scales
+    from oracle import ops
+
+    torch.manual_seed(0)
+    w = torch.randn(3, 256, 768) * 0.02
+    q, s = quantize_fp8_blockwise(w)
+    q2, s2 = ops.quantize_fp8_blockwise(w)
+    assert torch.equal(q, q2) and torch.equal(s, s2) and s.shape == (3, 2, 6)
+    full = ops.dequant_w8(q[1], s[1], 128, 128)
+    assert float((full - w[1]).abs().max()) < 0.02 * 4 / 8          # e4m3: 3 mantissa bits
+    s64 = reblock_scales(reblock_scales(s, 128, 64, 1), 128, 64, 2)
+    assert torch.equal(ops.dequant_w8(q[1], s64[1], 64, 64), full)
+    for rank in range(4):                                            # contracted-dim shards of 192 columns
+        lo, hi = rank * 192, (rank + 1) * 192
+        shard = ops.dequant_w8(q[1][:, lo:hi].contiguous(), s64[1][:, lo // 64:hi // 64].contiguous(), 64, 64)
+        assert torch.equal(shard, full[:, lo:hi])
+    with pytest.raises(ValueError):
+        reblock_scales(s, 128, 48, 1)
+
+
+def test_moe_expert_sharding_matches_the_reference_partition():
+    """make_moe_weights: rank r keeps intermediate columns [r*I/tp, (r+1)*I/tp) of EVERY expert -- gate rows and up
+    rows of w1, contracted columns of w2 (lite_llama/models/weights.py:129-130) -- so the per-rank partial outputs
+    sum to the unsharded block's output (checked with the oracle's fused_moe in fp32-friendly fp16)."""
+    from lite_llama_b200.executor.decoder import make_moe_weights
+    from oracle import ops
+
+    cfg = PRESETS["tiny-qwen3-moe"]
+    g = torch.Generator().manual_seed(1)
+    e, im, h = cfg.num_experts, cfg.moe_intermediate_size, cfg.hidden_size
+    router, gate, up, down = (torch.randn(*sh, generator=g) * 0.05 for sh in ((e, h), (e, im, h), (e, im, h), (e, h, im)))
+    x = (torch.randn(5, h, generator=g) * 0.5).half()
+    full = make_moe_weights(cfg, router, gate, up, down, "fp16", 1, 0, torch.float16)
+    w, ids = ops.route_topk(x, full.router, cfg.num_experts_per_tok, True)
+    want = ops.fused_moe(x, full.w1, full.w2, w, ids).float()
+    parts = []
+    for r in range(2):
+        m = make_moe_weights(cfg, router, gate, up, down, "fp16", 2, r, torch.float16)
+        assert m.w1.shape == (e, im, h) and m.w2.shape == (e, h, im // 2)
+        parts.append(ops.fused_moe(x, m.w1, m.w2, w, ids).float())
+    torch.testing.assert_close(parts[0] + parts[1], want, rtol=2e-2, atol=2e-3)
+    m8 = make_moe_weights(cfg, router, gate, up, down, "fp8", 4, 1, torch.float16)     # 128 / 4 = 32 columns per rank
+    assert m8.group_n == 32 and m8.group_k == 32 and m8.w1.dtype == torch.uint8
+    assert m8.w1_scale.shape == (e, 2, h // 32) and m8.w2_scale.shape == (e, h // 32, 1)

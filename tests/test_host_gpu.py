@@ -45,7 +45,8 @@ def _decidable_equal(got_logits, ref_logits, margin=8e-2):
 
 
 @pytest.mark.parametrize("name,quant", [("tiny-llama", None), ("tiny-llama", "int4"), ("tiny-qwen2", "int8"),
-                                        ("tiny-qwen2", "fp8"), ("tiny-qwen3", "smoothquant"), ("tiny-qwen3", None)])
+                                        ("tiny-qwen2", "fp8"), ("tiny-qwen3", "smoothquant"), ("tiny-qwen3", None),
+                                        ("tiny-qwen3-moe", None), ("tiny-qwen3-moe", "fp8")])
 def test_prefill_then_decode_matches_the_cpu_restatement(name, quant):
     cfg, runner, cpu = _build(name, quant)
     B, P = 3, 12

@@ -296,6 +296,36 @@ def test_flash_decoding_llama3_shape_long_context():
     close(out, ref, **ATT_TOL)
 
 
+def test_rope_kv_write_equals_rope_then_cache_write():
+    """The fused launch (rope on q/k where they lie + K|V cache write) against the two-step path the reference takes
+    (rope_emb_forward, then torch.cat + update_kv_buffer: models/base.py:76-79,228) -- bit for bit, on the strided
+    views of one fused-qkv buffer, prefill rectangle and decode step, scattered cache rows, int32/int64 indices."""
+    for (B, S, hq, hkv, d, idx_dtype) in [(3, 5, 8, 2, 64, torch.int32), (32, 1, 32, 8, 128, torch.int64),
+                                         (1, 1, 14, 2, 64, torch.int32), (2, 130, 4, 4, 32, torch.int32)]:
+        T = B * S
+        qkv = torch.randn(T, (hq + 2 * hkv) * d, device="cuda", dtype=torch.float16)
+        cos = torch.randn(B, S, d, device="cuda", dtype=torch.float16)
+        sin = torch.randn(B, S, d, device="cuda", dtype=torch.float16)
+        rows = torch.randperm(4 * T, device="cuda")[:T].to(idx_dtype)
+        pool_a = torch.zeros(4 * T, 2 * hkv, d, device="cuda", dtype=torch.float16)
+        pool_b = torch.zeros_like(pool_a)
+
+        def views(buf):
+            return (buf[:, : hq * d].view(T, hq, d), buf[:, hq * d : (hq + hkv) * d].view(T, hkv, d),
+                    buf[:, (hq + hkv) * d :].view(T, hkv, d))
+
+        a, b = qkv.clone(), qkv.clone()
+        qa, ka, va = views(a)
+        K().rope_emb_inplace(qa, ka, cos, sin, B, S)
+        K().update_kv_buffer_split(ka, va, rows, pool_a)
+        qb, kb, vb = views(b)
+        K().rope_kv_write(qb, kb, vb, cos, sin, rows, pool_b, B, S)
+        assert torch.equal(a, b), "rotated q/k differ"
+        assert torch.equal(pool_a, pool_b), "cache rows differ"
+        ref_q = ops.rope_half_split(views(qkv.cpu())[0], cos.cpu(), sin.cpu(), B, S)
+        close(qb.cpu(), ref_q, rtol=2e-3, atol=2e-3)
+
+
 # --------------------------------------------------------------------------- #
 # flash_attention2_no_pad
 # --------------------------------------------------------------------------- #
