@@ -106,7 +106,7 @@ int b2l_flash_decoding(void* out, const void* q, const void* k_cache, const void
                        int64_t q_head_stride, int64_t k_token_stride, int64_t k_head_stride, int64_t v_token_stride,
                        int64_t v_head_stride, int64_t table_batch_stride, int64_t table_seq_stride,
                        int64_t o_batch_stride, int64_t o_head_stride, void* workspace, int64_t workspace_bytes,
-                       int dtype, void* stream);
+                       void* tickets, int64_t num_tickets, int dtype, void* stream);
 
 /* flash_attention2_no_pad(q, k, v, sm_scale, b_start_loc, b_seq_len, max_seq_len)
  * -- lite_llama/kernels/flashattention2_nopad.py:175-231.  sm_scale already carries log2(e).  total_tokens = q.shape[0]
@@ -158,7 +158,10 @@ int b2l_w4a16_matmul(void* y, const void* x, const void* qweight, const void* sc
  *   qweight_packed int32 [N, K/8]: nibble position p of a word holds the K index [0,2,4,6,1,3,5,7][p] of that word
  *   table_packed   fp32 [ceil(N/128)][groups][128]: table_packed[t][g][r] = table[128 t + r][g], rows past N zero
  * b2l_w4a16_matmul_packed computes exactly b2l_w4a16_matmul's result from the repacked tensors; zeros_foldable = 1
- * promises that every zero point is an integer in [0, 1023] (checked once by the packer's caller). */
+ * promises that every zero point is an integer in [0, 1023] (checked once by the packer's caller).
+ * epilogue = 1 fuses swiglu_forward (lite_llama/kernels/swiglu.py:45-65; models/base.py:259-264 runs gate_proj,
+ * up_proj and swiglu as three launches): the packed rows must be interleaved (row 2i = gate_i, row 2i+1 = up_i);
+ * y is [m, n/2] = silu(gate) * up with both projections rounded to fp16 first, bit-identical to the unfused path. */
 int b2l_w4a16_pack_qweight(void* out, const void* in, int64_t n, int64_t k8, int64_t in_row_stride,
                            int64_t out_row_stride, void* stream);
 int b2l_w4a16_pack_table(void* out, const void* in, int64_t n, int64_t groups, int64_t row_stride,
@@ -167,7 +170,7 @@ int b2l_w4a16_matmul_packed(void* y, const void* x, const void* qweight_packed, 
                             const void* zeros_packed, const void* bias, int bias_is_f32, int64_t m, int64_t n,
                             int64_t k, int group_size, int zeros_foldable, int64_t x_row_stride,
                             int64_t qw_row_stride, int64_t y_row_stride, void* workspace, int64_t workspace_bytes,
-                            void* counters, int64_t num_counters, void* stream);
+                            void* counters, int64_t num_counters, int epilogue, void* stream);
 
 /* w8a16_matmul(x, qweight, scales, *, group_n, group_k, bias)
  * -- lite_llama/kernels/quantization/w8a16.py:155-216.  qweight uint8 (fp8-e4m3 bits) or int8. */

@@ -435,13 +435,15 @@ fa_tc_one_tile_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const float inv = 1.0f / lsum;
     mbar_wait(&ctl->o_full, 0);
     tc_fence_after();
-    if (row < seq_len) {
-      T* orow = reinterpret_cast<T*>(p.out) + (seq_start + row) * p.o_ts + (int64_t)head * p.o_hs;
+    // tcgen05.ld is warp-collective: every lane loads its row, only rows inside the sequence are stored
+    const bool row_ok = row < seq_len;
+    T* orow = reinterpret_cast<T*>(p.out) + (seq_start + (row_ok ? row : 0)) * p.o_ts + (int64_t)head * p.o_hs;
 #pragma unroll
-      for (int c = 0; c < kD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_base + 128u + c, v);
-        tc_wait_ld();
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(lane_base + 128u + c, v);
+      tc_wait_ld();
+      if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;

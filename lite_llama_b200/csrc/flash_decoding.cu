@@ -38,6 +38,7 @@ struct DecodeParams {
   void* out; int64_t o_bs, o_hs;
   float* ws_o;    // [B, Hq, splits, D]
   float* ws_lse;  // [B, Hq, splits]   (log2 domain)
+  int* tickets;   // one per (batch row, kv-head block), zero on entry and on exit; null = separate combine kernel
   int Hq, Hkv, G, qblocks;
   int HB;         // kv heads per CTA (divides Hkv)
   int copy_mode;  // 0: one copy per token (K|V fused run), 1: one K + one V copy, 2: one copy per head
@@ -257,6 +258,42 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) flash_decode_split_k
       }
     }
   }
+
+  // ---- stage 2 folded in (reference: a second kernel, flashdecoding.py:224-313): the CTA that finishes a
+  // (batch row, kv-head block) LAST merges its splits.  Deterministic: the merge always runs over all splits in index
+  // order, whoever executes it.  The ticket resets itself, so graph replays start clean. ----
+  if (p.splits > 1 && p.tickets != nullptr) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    int nsp = (int)((seq_len + p.chunk - 1) / p.chunk);          // splits that have tokens (the others returned above)
+    nsp = nsp < p.splits ? nsp : p.splits;
+    if (threadIdx.x == 0) {
+      int* t = p.tickets + (int64_t)b * gridDim.y + hblk;
+      const int old = atomicAdd(t, 1);
+      s_last = (old == nsp - 1);
+      if (s_last) *t = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int heads_here = p.HB * p.G;
+      const int head0 = hblk * p.HB * p.G;
+      for (int idx = threadIdx.x; idx < heads_here * D; idx += blockDim.x) {
+        const int head = head0 + idx / D, d = idx % D;
+        const int64_t off = ((int64_t)b * p.Hq + head) * p.splits;
+        float M = -INFINITY;
+        for (int sp = 0; sp < nsp; ++sp) M = fmaxf(M, __ldcg(p.ws_lse + off + sp));
+        float acc = 0.f, L = 0.f;
+        for (int sp = 0; sp < nsp; ++sp) {
+          const float w = fast_exp2(__ldcg(p.ws_lse + off + sp) - M);
+          acc += w * __ldcg(p.ws_o + (off + sp) * D + d);
+          L += w;
+        }
+        reinterpret_cast<T*>(p.out)[(int64_t)b * p.o_bs + (int64_t)head * p.o_hs + d] = from_f32<T>(acc / L);
+      }
+    }
+  }
 }
 
 // Stage 2: log-sum-exp merge of the per-split partials (reference: flashdecoding.py:224-313).
@@ -329,7 +366,7 @@ int launch_decode(const DecodeParams& p, const Plan& pl, int64_t batch, cudaStre
   const int threads = (p.HB * p.qblocks + 1) * 32;
   b2l_launch(flash_decode_split_kernel<T, D>, dim3(grid), dim3(threads), (size_t)(pl.smem), st, p);
   B2L_LAUNCH_CHECK();
-  if (p.splits > 1) {
+  if (p.splits > 1 && p.tickets == nullptr) {
     dim3 g2((unsigned)batch, (unsigned)p.Hq);
     b2l_launch(flash_decode_combine_kernel<T, D>, dim3(g2), dim3(D >= 128 ? 128 : 64), (size_t)(0), st, p);
     B2L_LAUNCH_CHECK();
@@ -354,8 +391,8 @@ extern "C" int b2l_flash_decoding(void* out, const void* q, const void* k_cache,
                                   int64_t q_batch_stride, int64_t q_head_stride, int64_t k_token_stride,
                                   int64_t k_head_stride, int64_t v_token_stride, int64_t v_head_stride,
                                   int64_t table_batch_stride, int64_t table_seq_stride, int64_t o_batch_stride,
-                                  int64_t o_head_stride, void* workspace, int64_t workspace_bytes, int dtype,
-                                  void* stream) {
+                                  int64_t o_head_stride, void* workspace, int64_t workspace_bytes, void* tickets,
+                                  int64_t num_tickets, int dtype, void* stream) {
   B2L_REQUIRE(out && q && k_cache && v_cache && b_req_tokens_table && b_req_idx && b_seq_len,
               "flash_decoding: null pointer");
   B2L_REQUIRE(num_q_heads > 0 && num_kv_heads > 0 && num_q_heads % num_kv_heads == 0,
@@ -389,6 +426,8 @@ extern "C" int b2l_flash_decoding(void* out, const void* q, const void* k_cache,
                          (const char*)v_cache == (const char*)k_cache + (int64_t)num_kv_heads * head_dim * 2;
   p.copy_mode = fused_run ? 0 : (heads_packed ? 1 : 2);
   p.ws_o = nullptr; p.ws_lse = nullptr;
+  // the split CTAs merge their own results when the caller provides zeroed tickets (one per batch row x head block)
+  p.tickets = (tickets && num_tickets >= batch * (num_kv_heads / pl.HB)) ? (int*)tickets : nullptr;
   if (pl.splits > 1) {
     const int64_t need = b2l_flash_decoding_workspace_bytes(batch, num_q_heads, num_kv_heads, head_dim, max_seq_len);
     B2L_REQUIRE(workspace && workspace_bytes >= need, "flash_decoding: workspace too small (%lld < %lld)",

@@ -72,6 +72,7 @@ struct QuantParams {
   int max_groups;                          // scale groups one CTA's k-range can touch (sizes the smem scale table)
   int aligned;                             // no segment spans two raw blocks (two MMA warps may alternate blocks)
   int zeros_foldable;                      // packed layout: the packer verified that every zero point is an integer in [0, 1023]
+  int swiglu;                              // epilogue: rows are (gate_i, up_i) pairs; y[m, i] = silu(gate) * up (N/2 columns)
   long long* timeline;                     // debug: [16][256] clock64 stamps of CTA (0,0,0), or null
   int debug;                               // debug experiments (timing only, results are wrong): see DBG_*
 };
@@ -118,6 +119,9 @@ struct __align__(8) QControl {
   uint64_t tab_full;                       // packed layout: the scale / zero-point tables have landed (bulk copies)
   uint32_t tmem_base;
   int is_last;
+  // tiles this CTA finished last (stream-K / split-K): reduced by ALL threads after the role loops
+  int nfix;
+  int fix_tile[4], fix_ntile[4], fix_sharers[4];
 };
 static_assert(sizeof(QControl) <= 1024, "control block too large");
 
@@ -237,6 +241,17 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// same approximate ops as elementwise.cu's swiglu (Triton's lowering of tl.sigmoid on sm_100a)
+__device__ __forceinline__ float ex2_approx_q(float x) {
+  float r;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float div_full_q(float a, float b) {
+  float r;
+  asm("div.full.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ float lds_f32(const float* p) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
@@ -530,25 +545,17 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   if (warp == kWarpWProd) {
     if (lane == 0) {
+      // Order matters for the launch latency of the short GEMMs (a CTA of the qkv / o projections converts 3-5 raw
+      // blocks in all): only what the first requests need is initialised before they are issued -- the weight ring's
+      // barriers, the tables, the first ring-full of weights -- and the other ~30 barriers afterwards (the device
+      // timeline showed the first weight request leaving 2400 cycles after kernel entry, most of it this lane's set-up).
       tma_prefetch_desc(&tmap_w);
-      tma_prefetch_desc(&tmap_x);
       for (int s = 0; s < p.w_stages; ++s) {
         mbar_init(&ctl->w_full[s], 1);
         mbar_init(&ctl->w_empty[s], 4);        // the 4 dequant warps that convert the block
       }
-      for (int s = 0; s < p.x_stages; ++s) {
-        mbar_init(&ctl->x_full[s], 1);
-        mbar_init(&ctl->x_empty[s], 1);        // tcgen05.commit of the MMA warp that issued the block
-      }
-      for (int s = 0; s < kOpStages; ++s) {
-        mbar_init(&ctl->op_full[s], 4);
-        mbar_init(&ctl->op_empty[s], 1);
-      }
-      for (int s = 0; s < NB; ++s) {
-        mbar_init(&ctl->acc_full[s], 1);
-        mbar_init(&ctl->acc_empty[s], 4);
-      }
       if (LAYOUT == 1) mbar_init(&ctl->tab_full, 1);
+      ctl->nfix = 0;
       mbar_fence_init();
       fence_proxy_async_smem();
       if (LAYOUT == 1) {
@@ -588,6 +595,24 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (LAYOUT == 0) asm volatile("bar.sync 5, %0;" ::"n"((kFillWarps + 1) * 32) : "memory");
     const int pre = nrb < p.w_stages ? nrb : p.w_stages;
     for (int i = 0; i < pre; ++i) w_issue(false);
+    if (lane == 0) {
+      // the rest of the set-up, behind the first requests; published to the other warps by the set-up barrier below
+      tma_prefetch_desc(&tmap_x);
+      for (int s = 0; s < p.x_stages; ++s) {
+        mbar_init(&ctl->x_full[s], 1);
+        mbar_init(&ctl->x_empty[s], 1);        // tcgen05.commit of the MMA warp that issued the block
+      }
+      for (int s = 0; s < kOpStages; ++s) {
+        mbar_init(&ctl->op_full[s], 4);
+        mbar_init(&ctl->op_empty[s], 1);
+      }
+      for (int s = 0; s < NB; ++s) {
+        mbar_init(&ctl->acc_full[s], 1);
+        mbar_init(&ctl->acc_empty[s], 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
   }
   if (warp == kWarpMma0) {
     tmem_alloc(&ctl->tmem_base, kTmemCols);
@@ -825,10 +850,28 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (tl && warp == kWarpEpi0 && lane == 0 && pi == wr.npieces - 1) tl[kTlMisc + 5] = clock64();
       pdl_wait_prior();              // output / workspace buffers may still be in use by the previous kernel
       auto store_final = [&]() {
-        if (!n_ok) return;
         float bv = 0.f;
-        if (p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
-                                       : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+        if (n_ok && p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
+                                               : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+        if (p.swiglu) {
+          // SiLU(gate) * up in the epilogue (reference: two GEMMs + swiglu_forward, models/base.py:259-264,
+          // kernels/swiglu.py:45-65).  The weight rows were interleaved at load time (row 2i = gate_i, 2i+1 = up_i), so
+          // the pair sits in neighbouring lanes.  Both projections are rounded to fp16 first -- exactly the values the
+          // unfused path writes to memory -- and the activation uses the swiglu kernel's arithmetic: bit-identical.
+#pragma unroll
+          for (int j = 0; j < BT; ++j) {
+            const float mine = __half2float(__float2half_rn(acc[j] + bv));
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const int m = m_tile * BT + j;
+            if (n_ok && (epi_tid & 1) == 0 && m < p.M) {
+              const float e = ex2_approx_q(-mine * 1.4426950408889634f);
+              const float sl = mine * div_full_q(1.0f, 1.0f + e);
+              y[(int64_t)m * p.ldy + (n >> 1)] = __float2half_rn(sl * other);
+            }
+          }
+          return;
+        }
+        if (!n_ok) return;
 #pragma unroll
         for (int j = 0; j < BT; ++j) {
           const int m = m_tile * BT + j;
@@ -857,14 +900,27 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
         for (int j = 0; j < BT; ++j) mine[j * kBlockW + epi_tid] = __float_as_uint(acc[j]);
         if (splitk_ticket(p.counters, tile_id, sharers, epi_tid, &ctl->is_last)) {
+          // Last finisher of the tile.  The partial sums are added up by ALL 512 threads once the role loops are over
+          // (end of the kernel): 128 epilogue threads walking the slots one after the other made the tail of the
+          // short GEMMs ~5 us long (per-CTA wall clock, profiles/r1b_cta_wallclock.txt).  Only when the small list is
+          // full (more than 4 finished tiles per CTA: tiny K) is the tile reduced right here.
+          const int f = ctl->nfix;             // written by epi_tid 0 only ...
+          asm volatile("bar.sync 2, 128;" ::: "memory");   // ... after every epilogue thread has read it
+          if (f < 4) {
+            if (epi_tid == 0) {
+              ctl->fix_tile[f] = tile_id; ctl->fix_ntile[f] = pc.n_tile; ctl->fix_sharers[f] = sharers;
+              ctl->nfix = f + 1;               // next read: behind the barriers of the next tile's ticket
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < BT; ++j) acc[j] = 0.f;
-          for (int s = 0; s < sharers; ++s) {
-            const uint32_t* src = base + (size_t)s * (BT * kBlockW) + epi_tid;
+            for (int j = 0; j < BT; ++j) acc[j] = 0.f;
+            for (int s = 0; s < sharers; ++s) {
+              const uint32_t* src = base + (size_t)s * (BT * kBlockW) + epi_tid;
 #pragma unroll
-            for (int j = 0; j < BT; ++j) acc[j] += __uint_as_float(__ldcg(src + j * kBlockW));
+              for (int j = 0; j < BT; ++j) acc[j] += __uint_as_float(__ldcg(src + j * kBlockW));
+            }
+            store_final();
           }
-          store_final();
         }
       }
 #pragma unroll
@@ -1022,6 +1078,46 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  // ---- split tiles this CTA finished last: out = sum of the partial tiles in slot order (deterministic) + bias ----
+  {
+    const int nfix = ctl->nfix;
+    const int slots_per_tile = p.sk_ctas > 0 ? p.sk_slots : p.splits;
+    constexpr int JT = kQuantThreads / kBlockW;            // token rows covered per pass (4)
+    constexpr int NJ = BT / JT;
+    const int n_local = threadIdx.x % kBlockW, j_first = threadIdx.x / kBlockW;
+    for (int f = 0; f < nfix; ++f) {
+      const int sharers = ctl->fix_sharers[f];
+      const uint32_t* base = p.ws + (size_t)ctl->fix_tile[f] * slots_per_tile * (BT * kBlockW) + n_local;
+      float sum[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) sum[i] = 0.f;
+      for (int s0 = 0; s0 < sharers; ++s0) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i)
+          sum[i] += __uint_as_float(__ldcg(base + (size_t)s0 * (BT * kBlockW) + (j_first + i * JT) * kBlockW));
+      }
+      const int n = ctl->fix_ntile[f] * kBlockW + n_local;
+      const bool n_ok = n < p.N;
+      float bv = 0.f;
+      if (n_ok && p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
+                                             : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+      __half* yy = reinterpret_cast<__half*>(p.y);
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const int m = blockIdx.y * BT + j_first + i * JT;
+        if (p.swiglu) {                                      // same arithmetic as store_final (neighbouring lanes = a pair)
+          const float mine = __half2float(__float2half_rn(sum[i] + bv));
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          if (n_ok && (n_local & 1) == 0 && m < p.M) {
+            const float e = ex2_approx_q(-mine * 1.4426950408889634f);
+            yy[(int64_t)m * p.ldy + (n >> 1)] = __float2half_rn(mine * div_full_q(1.0f, 1.0f + e) * other);
+          }
+        } else if (n_ok && m < p.M) {
+          yy[(int64_t)m * p.ldy + n] = __float2half_rn(sum[i] + bv);
+        }
+      }
+    }
+  }
   if (tl && threadIdx.x == 0) tl[kTlMisc + 6] = clock64();
   if (timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
     unsigned long long gt;
@@ -1192,6 +1288,7 @@ static int quant_common(int qk, QuantParams& p, SplitPlan& pl, void* y, const vo
   if ((g_debug & DBG_HALF_RING) && p.w_stages >= 4) p.w_stages = (p.w_stages / 2) & ~1;
   p.timeline = g_timeline;
   p.debug = g_debug;
+  p.swiglu = 0;
   p.zeros_foldable = 0;
   p.x = x; p.ldx = x_row_stride;
   p.force_xsum = 0; p.seg_shift = 0;
@@ -1303,7 +1400,8 @@ extern "C" int b2l_w4a16_matmul_packed(void* y, const void* x, const void* qweig
                                        const void* zeros_packed, const void* bias, int bias_is_f32, int64_t m,
                                        int64_t n, int64_t k, int group_size, int zeros_foldable, int64_t x_row_stride,
                                        int64_t qw_row_stride, int64_t y_row_stride, void* workspace,
-                                       int64_t workspace_bytes, void* counters, int64_t num_counters, void* stream) {
+                                       int64_t workspace_bytes, void* counters, int64_t num_counters, int epilogue,
+                                       void* stream) {
   B2L_REQUIRE(y && x && qweight_packed && scales_packed && zeros_packed, "w4a16_matmul_packed: null pointer");
   B2L_REQUIRE(m >= 0 && n > 0 && k > 0 && k % 8 == 0, "w4a16_matmul_packed: bad shape m=%lld n=%lld k=%lld",
               (long long)m, (long long)n, (long long)k);
@@ -1323,6 +1421,9 @@ extern "C" int b2l_w4a16_matmul_packed(void* y, const void* x, const void* qweig
   p.scales = (const float*)scales_packed; p.zeros = (const float*)zeros_packed; p.s_stride_n = 0; p.s_stride_k = 0;
   p.group_n = 1; p.group_k = group_size;
   p.zeros_foldable = zeros_foldable ? 1 : 0;
+  B2L_REQUIRE(epilogue == 0 || epilogue == 1, "w4a16_matmul_packed: epilogue %d (0 = none, 1 = swiglu over interleaved rows)", epilogue);
+  B2L_REQUIRE(epilogue == 0 || n % 2 == 0, "w4a16_matmul_packed: the swiglu epilogue needs an even number of rows");
+  p.swiglu = epilogue;
   return launch_q<Q_INT4>(tw, tx, p, pl, (cudaStream_t)stream, 1);
 }
 

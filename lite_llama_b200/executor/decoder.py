@@ -171,9 +171,10 @@ def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda",
             gu = torch.cat([wg[rank * inter:(rank + 1) * inter], wu[rank * inter:(rank + 1) * inter]], dim=0)
             dn = wd[:, rank * inter:(rank + 1) * inter]
 
-        def pack(w, b=None):
+        def pack(w, b=None, fuse_swiglu=False):
             w = w.contiguous()
-            return make_linear_weights(w.to(dtype) if method == "fp16" else w.to(dtype).float(), method, b, group_size)
+            return make_linear_weights(w.to(dtype) if method == "fp16" else w.to(dtype).float(), method, b, group_size,
+                                       fuse_swiglu=fuse_swiglu)
 
         lw = LayerWeights(
             input_norm=torch.ones(h, device=device, dtype=dtype), post_norm=torch.ones(h, device=device, dtype=dtype),
@@ -186,7 +187,7 @@ def random_weights(cfg: ModelConfig, method: str = "fp16", device: str = "cuda",
             lw.moe = make_moe_weights(cfg, router, gate, up, down, method, tp, rank, dtype)
             del gate, up, down
         else:
-            lw.gate_up, lw.down = pack(gu), pack(dn)
+            lw.gate_up, lw.down = pack(gu, fuse_swiglu=True), pack(dn)
             del wg, wu, wd, gu, dn
         if cfg.use_qk_norm:
             lw.q_norm = torch.ones(d, device=device, dtype=dtype)
@@ -268,7 +269,8 @@ class Decoder:
             down = self._moe(hidden.view(tokens, -1), lw.moe)                           # qwen3_moe.py:102-111 (partial)
             return down.view(batch, seq_len, -1), residual
         gu = apply_linear(hidden.view(tokens, -1), lw.gate_up)                          # base.py:263-264
-        act = swiglu_forward(gu[:, : self.inter], gu[:, self.inter :])
+        # W4A16: the activation already ran in the GEMM epilogue (row-interleaved gate|up), gu is [tokens, inter]
+        act = gu if lw.gate_up.swiglu else swiglu_forward(gu[:, : self.inter], gu[:, self.inter :])
         down = apply_linear(act, lw.down)                                               # partial: reduced by the next norm
         return down.view(batch, seq_len, -1), residual
 

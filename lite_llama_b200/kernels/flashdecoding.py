@@ -3,9 +3,13 @@
 
 from __future__ import annotations
 
+import os
+
 import torch
 
-from ._common import check, dtype_code, index_width, lib, ptr, require_cuda, stream_handle, workspace
+from ._common import check, dtype_code, index_width, lib, ptr, require_cuda, stream_handle, workspace, counters
+
+_FOLD = os.environ.get("B2L_FD_FOLD", "1") != "0"
 
 
 @torch.no_grad()
@@ -36,6 +40,9 @@ def flash_decoding(
     max_len = int(max_actual_seq_len)
     nbytes = lib().b2l_flash_decoding_workspace_bytes(batch, num_heads, num_kv_heads, head_dim, max_len)
     ws = workspace(nbytes, q.device)
+    # zeroed, self-resetting tickets: the split CTA that finishes a (row, head block) last merges the splits itself
+    # (no second launch); B2L_FD_FOLD=0 keeps the separate combine kernel for A/B measurements
+    cnt = counters(q.device) if _FOLD else None
     check(
         lib().b2l_flash_decoding(
             out.data_ptr(), q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), b_req_tokens_table.data_ptr(),
@@ -44,7 +51,7 @@ def flash_decoding(
             batch, num_heads, num_kv_heads, head_dim, max_len, float(qk_scale),
             q.stride(0), q.stride(1), k_cache.stride(0), k_cache.stride(1), v_cache.stride(0), v_cache.stride(1),
             b_req_tokens_table.stride(0), b_req_tokens_table.stride(1), out.stride(0), out.stride(1),
-            ptr(ws), nbytes, code, stream_handle(),
+            ptr(ws), nbytes, ptr(cnt), cnt.numel() if cnt is not None else 0, code, stream_handle(),
         )
     )
     return out

@@ -113,8 +113,13 @@ def w4a16_pack(qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor,
 
 
 @torch.no_grad()
-def w4a16_matmul_packed(x: torch.Tensor, packed: PackedW4, *, bias: torch.Tensor | None = None) -> torch.Tensor:
-    """:func:`w4a16_matmul` on a :class:`PackedW4` (same result, bit for bit in the integer unpack)."""
+def w4a16_matmul_packed(x: torch.Tensor, packed: PackedW4, *, bias: torch.Tensor | None = None,
+                        swiglu: bool = False) -> torch.Tensor:
+    """:func:`w4a16_matmul` on a :class:`PackedW4` (same result, bit for bit in the integer unpack).
+
+    ``swiglu=True``: the packed rows are interleaved ``(gate_0, up_0, gate_1, up_1, ...)`` (see
+    :func:`interleave_gate_up`) and the GEMM's epilogue applies ``silu(gate) * up``; the result is ``[..., N/2]``
+    and equals ``swiglu_forward`` of the two separate projections bit for bit."""
     if x.dtype != torch.float16:
         raise ValueError(f"w4a16 activations must be fp16, got {x.dtype}")
     require_cuda(x, bias)
@@ -126,7 +131,8 @@ def w4a16_matmul_packed(x: torch.Tensor, packed: PackedW4, *, bias: torch.Tensor
     if a.stride(-1) != 1 or a.stride(0) % 8 != 0 or a.data_ptr() % 16 != 0:
         a = a.contiguous()
     m = a.shape[0]
-    out = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    n_out = n // 2 if swiglu else n
+    out = torch.empty((m, n_out), dtype=x.dtype, device=x.device)
     bias_f32 = 0
     if bias is not None:
         if bias.dtype == torch.float32:
@@ -143,7 +149,15 @@ def w4a16_matmul_packed(x: torch.Tensor, packed: PackedW4, *, bias: torch.Tensor
         L.b2l_w4a16_matmul_packed(
             out.data_ptr(), a.data_ptr(), packed.qweight.data_ptr(), packed.scales.data_ptr(), packed.zeros.data_ptr(),
             ptr(bias), bias_f32, m, n, k, packed.group_size, 1 if packed.zeros_foldable else 0, a.stride(0),
-            packed.qweight.stride(0), out.stride(0), ptr(ws), nbytes, cnt.data_ptr(), cnt.numel(), stream_handle(),
+            packed.qweight.stride(0), out.stride(0), ptr(ws), nbytes, cnt.data_ptr(), cnt.numel(), 1 if swiglu else 0,
+            stream_handle(),
         )
     )
-    return out.reshape(*leading, n)
+    return out.reshape(*leading, n_out)
+
+
+def interleave_gate_up(t: torch.Tensor) -> torch.Tensor:
+    """Rows ``[gate_0..gate_{I-1}, up_0..up_{I-1}]`` -> ``[gate_0, up_0, gate_1, up_1, ...]`` (any row-wise tensor of
+    the gate|up projection: packed weights, scales, zero points, bias). Load-time only."""
+    half = t.shape[0] // 2
+    return torch.stack([t[:half], t[half:]], dim=1).reshape(t.shape).contiguous()

@@ -13,6 +13,7 @@ from dataclasses import dataclass
 import torch
 
 from ..kernels import PackedW4, linear, smoothquant_matmul, w4a16_matmul, w4a16_matmul_packed, w4a16_pack, w8a16_matmul
+from ..kernels.quantization import interleave_gate_up
 from .params import quantize_fp8_per_channel, quantize_int4_groupwise, quantize_int8_per_channel
 
 LINEAR_METHODS = ("fp16", "int4", "int8", "fp8", "smoothquant")
@@ -32,6 +33,7 @@ class LinearWeights:
     bias: torch.Tensor | None = None
     group_size: int = 128
     packed: PackedW4 | None = None          # int4: kernel-native repack (replaces qweight/scales/zeros)
+    swiglu: bool = False                    # gate|up projection stored row-interleaved: the GEMM applies silu(gate) * up
 
     def nbytes(self) -> int:
         total = 0
@@ -44,7 +46,7 @@ class LinearWeights:
 
 
 def make_linear_weights(weight: torch.Tensor, method: str, bias: torch.Tensor | None = None,
-                        group_size: int = 128) -> LinearWeights:
+                        group_size: int = 128, fuse_swiglu: bool = False) -> LinearWeights:
     """Convert a float ``[N, K]`` weight into ``method``'s storage (the ``--quantization`` path of the
     reference: methods/w4a16.py:39-43, w8a16.py:95-112, w8a8.py:30-37)."""
     n, k = weight.shape
@@ -55,8 +57,12 @@ def make_linear_weights(weight: torch.Tensor, method: str, bias: torch.Tensor | 
         if q.is_cuda and os.environ.get("B2L_W4_LAYOUT", "packed") != "reference":
             # load-time repack into the kernel-native layout (the reference's `_layout` seam); the reference-layout
             # tensors are not kept, so a projection is stored exactly once
+            fuse = fuse_swiglu and n % 2 == 0 and os.environ.get("B2L_FUSE_SWIGLU", "1") != "0"
+            if fuse:   # [gate | up] rows -> (gate_i, up_i) pairs: the GEMM epilogue applies the activation
+                q, s, z = interleave_gate_up(q), interleave_gate_up(s), interleave_gate_up(z)
+                bias = interleave_gate_up(bias) if bias is not None else None
             return LinearWeights(method, n, k, bias=bias, group_size=group_size,
-                                 packed=w4a16_pack(q, s, z, group_size=group_size))
+                                 packed=w4a16_pack(q, s, z, group_size=group_size), swiglu=fuse)
         return LinearWeights(method, n, k, qweight=q, scales=s, zeros=z, bias=bias, group_size=group_size)
     if method in ("int8", "smoothquant"):
         q, s = quantize_int8_per_channel(weight)
@@ -73,7 +79,7 @@ def apply_linear(x: torch.Tensor, w: LinearWeights) -> torch.Tensor:
         return linear(x, w.weight, w.bias)
     if w.method == "int4":
         if w.packed is not None:
-            return w4a16_matmul_packed(x, w.packed, bias=w.bias)
+            return w4a16_matmul_packed(x, w.packed, bias=w.bias, swiglu=w.swiglu)
         return w4a16_matmul(x, w.qweight, w.scales, w.zeros, group_size=w.group_size, bias=w.bias)
     if w.method in ("int8", "fp8"):
         return w8a16_matmul(x, w.qweight, w.scales, group_n=1, group_k=w.in_features, bias=w.bias)

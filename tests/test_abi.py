@@ -52,7 +52,7 @@ def test_argument_validation_happens_on_the_host():
     rc = lib.b2l_update_kv_index(p, p, 3, p, 4, p, 4, 1, 1, 1, None)
     assert rc == -1 and b"widths" in lib.b2l_last_error()
     rc = lib.b2l_flash_decoding(p, p, p, p, p, p, 4, p, 4, 1, 6, 4, 64, 16, ctypes.c_float(0.1),
-                                64, 64, 64, 64, 64, 64, 1, 1, 64, 64, None, 0, 0, None)
+                                64, 64, 64, 64, 64, 64, 1, 1, 64, 64, None, 0, None, 0, 0, None)
     assert rc == -1 and b"multiple of num_kv_heads" in lib.b2l_last_error()
     rc = lib.b2l_w4a16_matmul(p, p, p, p, p, None, 0, 1, 8, 100, 128, 8, 8, 1, 1, 8, None, 0, None, 0, None)
     assert rc == -1 and b"w4a16_matmul" in lib.b2l_last_error()

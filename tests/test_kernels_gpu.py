@@ -296,6 +296,25 @@ def test_flash_decoding_llama3_shape_long_context():
     close(out, ref, **ATT_TOL)
 
 
+@pytest.mark.parametrize("m", [1, 32, 64, 200])
+def test_w4a16_swiglu_epilogue_is_bit_identical_to_gemm_then_swiglu(m):
+    """gate|up rows interleaved at load time + silu(gate) * up in the GEMM epilogue (stream-K fix-up path included:
+    N = 1024, K = 512 splits tiles across CTAs) against the unfused path: w4a16 GEMM, then swiglu_forward."""
+    from lite_llama_b200.kernels.quantization import interleave_gate_up
+
+    torch.manual_seed(m)
+    inter, k = 512, 512
+    w = torch.randn(2 * inter, k) * 0.05
+    qw, sc, zp = (t.cuda() for t in ops.quantize_int4_groupwise(w, 128))
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16)
+    gu = K().w4a16_matmul(x, qw, sc, zp, group_size=128)
+    want = K().swiglu_forward(gu[:, :inter], gu[:, inter:])
+    packed = K().w4a16_pack(interleave_gate_up(qw), interleave_gate_up(sc), interleave_gate_up(zp), group_size=128)
+    got = K().w4a16_matmul_packed(x, packed, swiglu=True)
+    assert got.shape == (m, inter)
+    assert torch.equal(got, want)
+
+
 def test_rope_kv_write_equals_rope_then_cache_write():
     """The fused launch (rope on q/k where they lie + K|V cache write) against the two-step path the reference takes
     (rope_emb_forward, then torch.cat + update_kv_buffer: models/base.py:76-79,228) -- bit for bit, on the strided
