@@ -349,7 +349,9 @@ __device__ __forceinline__ void issue_block(QControl* ctl, uint32_t tmem_base, u
 // LAYOUT (int4 only): 0 = the reference's tensors as they are; 1 = the load-time repack of b2l_w4a16_pack_* (nibbles
 // of a word interleaved so that one LOP3 extracts a K-consecutive pair, scale / zero tables tiled [tile][group][128
 // rows] so that a CTA's share is one contiguous bulk copy per piece).
-template <int QK, int BT, bool DBG, int LAYOUT>
+// EPI: 0 = store the projection; 1 = SiLU(gate) * up over row-interleaved gate|up weights (its own instantiation: the
+// activation code unrolled over the token tile grew the kernel by ~10 % and that alone slowed every GEMM, profiles/).
+template <int QK, int BT, bool DBG, int LAYOUT, int EPI = 0>
 __global__ void __launch_bounds__(kQuantThreads, 1)
 gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                   const QuantParams p) {
@@ -853,7 +855,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         float bv = 0.f;
         if (n_ok && p.bias) bv = p.bias_is_f32 ? reinterpret_cast<const float*>(p.bias)[n]
                                                : __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
-        if (p.swiglu) {
+        if (EPI == 1) {
           // SiLU(gate) * up in the epilogue (reference: two GEMMs + swiglu_forward, models/base.py:259-264,
           // kernels/swiglu.py:45-65).  The weight rows were interleaved at load time (row 2i = gate_i, 2i+1 = up_i), so
           // the pair sits in neighbouring lanes.  Both projections are rounded to fp16 first -- exactly the values the
@@ -1105,7 +1107,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
         const int m = blockIdx.y * BT + j_first + i * JT;
-        if (p.swiglu) {                                      // same arithmetic as store_final (neighbouring lanes = a pair)
+        if (EPI == 1) {                                      // same arithmetic as store_final (neighbouring lanes = a pair)
           const float mine = __half2float(__float2half_rn(sum[i] + bv));
           const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
           if (n_ok && (n_local & 1) == 0 && m < p.M) {
@@ -1239,10 +1241,10 @@ static inline int env_int(const char* name, int dflt) {
   return e && e[0] ? atoi(e) : dflt;
 }
 
-template <int QK, int BT, bool DBG, int LAYOUT>
+template <int QK, int BT, bool DBG, int LAYOUT, int EPI = 0>
 static int launch_q_inst(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
                          cudaStream_t st) {
-  auto kern = gemm_quant_kernel<QK, BT, DBG, LAYOUT>;
+  auto kern = gemm_quant_kernel<QK, BT, DBG, LAYOUT, EPI>;
   static int configured_smem = 0;
   if (pl.smem_bytes > configured_smem) {
     B2L_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
@@ -1260,8 +1262,13 @@ static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const Quant
                        cudaStream_t st, int layout) {
   const bool dbg = p.debug != 0 || p.timeline != nullptr;
   if constexpr (QK == Q_INT4) {
-    if (layout == 1)
+    if (layout == 1) {
+      if (p.swiglu) {
+        B2L_REQUIRE(!dbg, "w4a16_matmul_packed: the swiglu epilogue has no debug instantiation");
+        return launch_q_inst<QK, BT, false, 1, 1>(tw, tx, p, pl, st);
+      }
       return dbg ? launch_q_inst<QK, BT, true, 1>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, false, 1>(tw, tx, p, pl, st);
+    }
   }
   return dbg ? launch_q_inst<QK, BT, true, 0>(tw, tx, p, pl, st) : launch_q_inst<QK, BT, false, 0>(tw, tx, p, pl, st);
 }

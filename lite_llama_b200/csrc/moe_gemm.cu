@@ -38,6 +38,7 @@ struct MoeParams {
   int N, K, num_kb;
   int num_valid_slots, top_k;
   int raw_stages, max_groups;
+  int op_stages;                           // depth of the operand ring (<= kMoeOpStages)
 };
 
 struct __align__(8) MoeControl {
@@ -73,7 +74,7 @@ __device__ __forceinline__ uint4 moe_dequant8(uint32_t lo, uint32_t hi, bool fp8
 }
 
 template <int MK, int BT>
-__global__ void __launch_bounds__(kMoeThreads, 1)
+__global__ void __launch_bounds__(kMoeThreads, BT == 16 ? 2 : 1)
 moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -86,7 +87,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
   // op ring stage: [dequantised W tile (8-bit only)] [gathered X tile]
   constexpr int kOpStage = (MK == M_F16 ? 0 : kABytes) + kXBytes;
   uint8_t* op_ring = smem + 1024;
-  uint8_t* raw_ring = op_ring + kMoeOpStages * kOpStage;
+  uint8_t* raw_ring = op_ring + p.op_stages * kOpStage;
   float* scale_tab = reinterpret_cast<float*>(raw_ring + (size_t)p.raw_stages * kRawW);
   constexpr int kTmemCols = 2 * BT < 32 ? 32 : 2 * BT;
 
@@ -106,7 +107,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
       mbar_init(&ctl->raw_full[s], 1);
       mbar_init(&ctl->raw_empty[s], MK == M_F16 ? 1 : kMoeXformWarps);
     }
-    for (int s = 0; s < kMoeOpStages; ++s) {
+    for (int s = 0; s < p.op_stages; ++s) {
       mbar_init(&ctl->op_full[s], kMoeXformWarps);
       mbar_init(&ctl->op_empty[s], 1);
     }
@@ -148,7 +149,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
     constexpr uint32_t idesc = umma_idesc(1u, 0u, 0u, 0u, 0u, kBlockW, BT);
     const uint64_t op_desc0 = umma_desc_sw128_kmajor(smem_u32(op_ring));
     const uint64_t raw_desc0 = umma_desc_sw128_kmajor(smem_u32(raw_ring));
-    PipeState rs(p.raw_stages), os(kMoeOpStages);
+    PipeState rs(p.raw_stages), os(p.op_stages);
     const int seg_steps = seg_len / 16;
     int steps_left = steps_total;
     int seg_left = seg_steps < steps_left ? seg_steps : steps_left;
@@ -268,7 +269,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
       }
     }
     const int row = dt & 127, hsel = dt >> 7, rx = row & 7;   // conflict-free swizzled 16-byte accesses
-    PipeState rs(p.raw_stages), os(kMoeOpStages);
+    PipeState rs(p.raw_stages), os(p.op_stages);
     for (int i = 0; i < nkb; ++i) {
       const int sub = i % RW;
       mbar_wait(&ctl->op_empty[os.stage], os.phase ^ 1);
@@ -315,7 +316,7 @@ moe_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const MoeParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-struct MoePlan { int raw_stages, smem, max_groups; };
+struct MoePlan { int raw_stages, smem, max_groups, op_stages; };
 
 static MoePlan moe_plan(int mk, int bt, int64_t K, int seg_len) {
   MoePlan pl;
@@ -323,12 +324,34 @@ static MoePlan moe_plan(int mk, int bt, int64_t K, int seg_len) {
   const int rw = mk == M_F16 ? 1 : 2;
   const int op_stage = (mk == M_F16 ? 0 : kABytes) + bt * kStageKBytes;
   pl.max_groups = mk == M_F16 ? 0 : (int)((K + seg_len - 1) / seg_len) + 1;
-  const int fixed = 1024 + kMoeOpStages * op_stage + pl.max_groups * kBlockW * 4 + 1024;
-  int stages = (b2l_max_smem_optin() - fixed) / rawW;
   const int nkb = (int)cdiv64(K, 64);
-  if (stages > kMoeMaxRaw) stages = kMoeMaxRaw;
+  // Decode-sized blocks (16 slots): a CTA streams one 128-row weight tile of ONE expert and is gone -- thousands of
+  // short CTAs per launch (Qwen3-30B-A3B at 32 tokens: 115 touched experts x 12-16 tiles), each paying set-up, the
+  // first-byte latency and the epilogue alone when one CTA fills the SM.  A half-depth operand ring + 4 raw stages
+  // fit TWO CTAs per SM (<= 113 KiB, 64 registers per thread): one streams while the other starts or drains.
+  pl.op_stages = kMoeOpStages;
+  int cap = b2l_max_smem_optin();
+  int max_raw = kMoeMaxRaw;
+  if (bt == 16) {
+    pl.op_stages = 2;
+    cap = (b2l_max_smem_optin() + 1024) / 2 - 1024;     // two CTAs (+1 KiB reserved each) per SM
+    max_raw = 4;
+  }
+  const int fixed = 1024 + pl.op_stages * op_stage + pl.max_groups * kBlockW * 4 + 1024;
+  int stages = (cap - fixed) / rawW;
+  if (stages > max_raw) stages = max_raw;
   if (stages > nkb / rw + 1) stages = nkb / rw + 1;
-  if (stages < 2) stages = 2;
+  if (stages < 2) {   // does not fit twice: one CTA per SM with the full rings
+    pl.op_stages = kMoeOpStages;
+    const int fixed1 = 1024 + pl.op_stages * op_stage + pl.max_groups * kBlockW * 4 + 1024;
+    stages = (b2l_max_smem_optin() - fixed1) / rawW;
+    if (stages > kMoeMaxRaw) stages = kMoeMaxRaw;
+    if (stages > nkb / rw + 1) stages = nkb / rw + 1;
+    if (stages < 2) stages = 2;
+    pl.raw_stages = stages;
+    pl.smem = fixed1 + stages * rawW;
+    return pl;
+  }
   pl.raw_stages = stages;
   pl.smem = fixed + stages * rawW;
   return pl;
@@ -384,7 +407,7 @@ extern "C" int b2l_moe_gemm(void* c, const void* a, const void* w, int weight_ki
   p.group_n = (int)(group_n > 0 ? (group_n > n ? n : group_n) : 1); p.group_k = seg_len;
   p.N = (int)n; p.K = (int)k; p.num_kb = (int)cdiv64(k, 64);
   p.num_valid_slots = (int)num_valid_slots; p.top_k = top_k;
-  p.raw_stages = pl.raw_stages; p.max_groups = pl.max_groups;
+  p.raw_stages = pl.raw_stages; p.max_groups = pl.max_groups; p.op_stages = pl.op_stages;
   CUtensorMap tw;
   int rc;
   if (weight_kind == M_F16)

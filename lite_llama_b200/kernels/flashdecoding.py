@@ -9,7 +9,9 @@ import torch
 
 from ._common import check, dtype_code, index_width, lib, ptr, require_cuda, stream_handle, workspace, counters
 
-_FOLD = os.environ.get("B2L_FD_FOLD", "1") != "0"
+# Folding the split-KV merge into the last-arriving split CTA (tickets) removes a launch but measured SLOWER at decode
+# sizes (24.8 us vs 11.3 + ~3 us: one CTA merges 4096 outputs serially at L2 latency, profiles/r2f_*): off by default.
+_FOLD = os.environ.get("B2L_FD_FOLD", "0") != "0"
 
 
 @torch.no_grad()
@@ -40,8 +42,8 @@ def flash_decoding(
     max_len = int(max_actual_seq_len)
     nbytes = lib().b2l_flash_decoding_workspace_bytes(batch, num_heads, num_kv_heads, head_dim, max_len)
     ws = workspace(nbytes, q.device)
-    # zeroed, self-resetting tickets: the split CTA that finishes a (row, head block) last merges the splits itself
-    # (no second launch); B2L_FD_FOLD=0 keeps the separate combine kernel for A/B measurements
+    # B2L_FD_FOLD=1: zeroed, self-resetting tickets; the split CTA that finishes a (row, head block) last merges the
+    # splits itself (no second launch)
     cnt = counters(q.device) if _FOLD else None
     check(
         lib().b2l_flash_decoding(

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--k", type=int, default=4096)
     ap.add_argument("--ctx", type=int, default=8192)
     ap.add_argument("--iters", type=int, default=4)
+    ap.add_argument("--swiglu", action="store_true", help="w4a16 packed: SiLU*up epilogue over interleaved rows")
     ap.add_argument("--reference-layout", action="store_true", help="w4a16: the reference's tensors instead of the load-time repack")
     a = ap.parse_args()
     dev = "cuda"
@@ -34,7 +35,7 @@ def main():
                 fn = lambda: K.w4a16_matmul(x, qw, sc, zp, group_size=128)
             else:
                 pk = K.w4a16_pack(qw, sc, zp, group_size=128)
-                fn = lambda: K.w4a16_matmul_packed(x, pk)
+                fn = lambda: K.w4a16_matmul_packed(x, pk, swiglu=a.swiglu)
         elif a.op == "w8a16":
             qw = torch.randint(0, 120, (a.n, a.k), device=dev, dtype=torch.uint8)
             sc = torch.rand((a.n + 127) // 128, (a.k + 127) // 128, device=dev)
@@ -55,6 +56,29 @@ def main():
         seq = torch.full((B,), a.ctx, dtype=torch.int32, device=dev)
         req = torch.arange(B, dtype=torch.int32, device=dev)
         fn = lambda: K.flash_decoding(q, pool[:, :hkv], pool[:, hkv:], 1 / math.sqrt(d), table, req, seq, a.ctx)
+    elif a.op == "prefill":
+        # causal varlen prefill, Llama-3-8B heads, q/k/v as views of one fused-qkv buffer
+        B, S, hq, hkv, d = a.m, a.ctx, 32, 8, 128
+        T = B * S
+        qkv = torch.randn(T, (hq + 2 * hkv) * d, device=dev, dtype=torch.float16) * 0.3
+        q = qkv[:, : hq * d].view(T, hq, d)
+        k = qkv[:, hq * d:(hq + hkv) * d].view(T, hkv, d)
+        v = qkv[:, (hq + hkv) * d:].view(T, hkv, d)
+        start = torch.arange(B, device=dev, dtype=torch.int32) * S
+        lens = torch.full((B,), S, dtype=torch.int32, device=dev)
+        fn = lambda: K.flash_attention2_no_pad(q, k, v, 1.4426950408889634 / math.sqrt(d), start, lens, S)
+    elif a.op == "moe":
+        # Qwen3-30B-A3B layer, fp8 experts with 128 x 128 block scales, a.m tokens
+        E, top_k, I, h, T = 128, 8, 768, 2048, a.m
+        hidden = torch.randn(T, h, device=dev, dtype=torch.float16) * 0.5
+        w1 = (torch.randn(E, 2 * I, h, device=dev) * 0.5).to(torch.float8_e4m3fn).view(torch.uint8)
+        w2 = (torch.randn(E, h, I, device=dev) * 0.5).to(torch.float8_e4m3fn).view(torch.uint8)
+        s1 = torch.rand(E, (2 * I + 127) // 128, h // 128, device=dev) * 0.01 + 0.005
+        s2 = torch.rand(E, h // 128, (I + 127) // 128, device=dev) * 0.01 + 0.005
+        tw, ti = torch.topk(torch.softmax(torch.randn(T, E, device=dev), -1), top_k, dim=-1)
+        tw = (tw / tw.sum(-1, keepdim=True)).to(torch.float16)
+        ti = ti.to(torch.int32)
+        fn = lambda: K.fused_moe(hidden, w1, w2, tw, ti, w1_scale=s1, w2_scale=s2, group_n=128, group_k=128)
     else:
         raise SystemExit(f"unknown op {a.op}")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
