@@ -202,3 +202,39 @@ def test_programmatic_dependent_launch_is_bit_identical():
         lib.b2l_set_pdl(old)
     graphed = run(1, True)
     assert torch.equal(serial, graphed)
+
+
+def test_one_llama3_8b_shape_layer_matches_the_cpu_restatement():
+    """Real projection shapes (hidden 4096, 32/8 heads of 128, intermediate 14336, W4A16 g128), one layer, small
+    vocabulary: prefill of a ragged batch then two decode steps -- at batch 3 and at the batch-1 shape that stalled in
+    round 1 -- against oracle/model.py with the same weights."""
+    from lite_llama_b200.executor import PRESETS, ModelRunner
+
+    cfg = PRESETS["llama-3-8b"].with_(num_layers=1, vocab_size=2048, max_seq_len=64)
+    embed, lm_head, layers = omodel.random_cpu_layers(cfg, "int4", 1, seed=0)
+    for lens_list in ([12, 7, 9], [11]):
+        B, P = len(lens_list), max(lens_list)
+        runner = ModelRunner.build(cfg, max_seq_len=64, max_gpu_num_blocks=B * 64, device="cuda", quantization="int4",
+                                   seed=0, draw_device="cpu")
+        cpu = omodel.CpuDecoder(cfg, embed, lm_head, layers, max_tokens=B * 64, max_pos=64, method="int4")
+        lens = torch.tensor(lens_list)
+        ids = torch.randint(0, cfg.vocab_size, (B, P), generator=torch.Generator().manual_seed(1))
+        pos = torch.arange(P).repeat(B, 1)
+        b_req = torch.arange(B)
+        sel = runner.prefill_alloc_kv_cache(P, lens.cuda(), b_req.cuda())
+        logits = runner.forward(ids.cuda(), pos.cuda())
+        table = runner.b_req_tokens_table.cpu().clone()
+        ref = cpu.forward(ids, pos, sel.cpu(), table, b_req, lens, (torch.arange(B) * P).to(torch.int32))
+        for i in range(B):
+            _check_logits(logits[i, : lens[i]], ref[i, : lens[i]])
+        cur = lens.clone()
+        tok = ref[torch.arange(B), lens - 1].argmax(-1)
+        for _ in range(2):
+            sel = runner.decode_alloc_kv_cache(B)
+            cur += 1
+            p1 = (cur - 1).view(B, 1)
+            out = runner.forward(tok.view(B, 1).cuda(), p1.cuda())
+            ref1 = cpu.forward(tok.view(B, 1), p1, sel.cpu(), runner.b_req_tokens_table.cpu().clone(), b_req, cur)
+            _check_logits(out, ref1)
+            tok = ref1[:, -1].argmax(-1)
+        del runner

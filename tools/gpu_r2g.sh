@@ -5,7 +5,7 @@ S=gpurun_out/r2g_summary.txt; rm -f $S
 run() { local name=$1 t=$2; shift 2
   timeout -s KILL $t "$@" > gpurun_out/r2g_$name.out 2> gpurun_out/r2g_$name.err
   echo "$name exit=$?" >> $S; }
-run quick_tests 150 python -m pytest -q -p no:cacheprovider -x --timeout 40 tests/test_kernels_gpu.py tests/test_host_gpu.py -m gpu -k "swiglu or moe or w4a16 or prefill_then_decode or flash_decoding"
+run quick_tests 150 python -m pytest -q -p no:cacheprovider -x --timeout 40 tests/test_kernels_gpu.py tests/test_host_gpu.py -m gpu -k "swiglu or moe or w4a16 or prefill_then_decode or flash_decoding or bs1 or llama3"
 run bench 200 python bench.py --steps 64 --warmup 4 --no-cpu-baseline
 run bench_noswiglu 200 env B2L_FUSE_SWIGLU=0 python bench.py --steps 64 --warmup 4 --no-cpu-baseline
 run bench_moe 300 python bench.py --model qwen3-30b-a3b --quant fp8 --steps 32 --warmup 4 --no-cpu-baseline --watchdog-s 280
