@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF-transformers-on-CPU row (configs[0])")
     ap.add_argument("--watchdog-s", type=int, default=600, help="give up (exit 3) after this many seconds; 0 = never")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-dp-line", action="store_true", help="N > 1, tp: skip the extra replica (weak-scaling) measurement")
     ap.add_argument("--cpu-layers", type=int, default=2, help="decoder layers in the CPU sample")
     return ap.parse_args()
 
@@ -484,6 +485,14 @@ def main() -> None:
             "limiting_collective": f"{n_ex} latency-bound {msg // 1024} KiB exchanges per step",
         }
 
+    # ---- the same GPUs as N independent replicas (no collective): a second, weak-scaling line beside the TP one ----
+    dp_info = None
+    if tp and not args.no_dp_line:
+        try:
+            dp_info = dp_replica_line(args, dev, rank, world, bucket, max_seq_len, K, W)
+        except Exception as ex:  # the TP headline must survive
+            dp_info = {"error": repr(ex)[:300]}
+
     if rank != 0:
         finish(world)
         return
@@ -521,6 +530,8 @@ def main() -> None:
     }
     if tp_info is not None:
         line["tensor_parallel"] = tp_info
+    if dp_info is not None:
+        line["dp_replicas"] = dp_info
     if not args.no_breakdown:
         try:
             kb = kernel_breakdown(runner, B, int(mean_ctx), hbm_peak)
@@ -554,6 +565,52 @@ def main() -> None:
             line["hf_cpu_baseline"] = {"error": repr(ex)[:300]}
     print(json.dumps(line), flush=True)
     finish(world)
+
+
+def dp_replica_line(args, dev, rank, world, bucket, max_seq_len, K, W) -> dict:
+    """Device-timed decode throughput of `world` independent full replicas (one per GPU, different seeds, no
+    collective) on the GPUs that just ran the tensor-parallel measurement: the weak-scaling reading of the same
+    hardware. Built while the tensor-parallel state is masked, so the captured graphs contain no exchange."""
+    import torch.distributed as dist
+
+    from lite_llama_b200.distributed import parallel_state
+    from lite_llama_b200.executor import ModelRunner
+    from lite_llama_b200.executor.model_runner import GreedyDecodeLoop
+
+    B, P = args.batch, args.prompt_len
+    saved = (parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM)
+    parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM = 1, 0, None
+    try:
+        runner = ModelRunner.build(args.model, max_seq_len=max_seq_len, max_gpu_num_blocks=B * max_seq_len, device=dev,
+                                   quantization=None if args.quant == "fp16" else args.quant, seed=100 + rank,
+                                   num_layers=args.layers)
+        gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+        prompts = torch.randint(0, runner.config.vocab_size, (B, P), generator=gen, device=dev)
+        lens = torch.full((B,), P, dtype=torch.int64, device=dev)
+        req = torch.arange(B, dtype=torch.int64, device=dev)
+        runner.prefill_alloc_kv_cache(P, lens.clone(), req)
+        first = runner.forward(prompts, torch.arange(P, device=dev).repeat(B, 1), last_token_index=lens - 1)[:, -1].argmax(-1)
+        loop = GreedyDecodeLoop(runner, B, bucket)
+        loop.begin(first, lens, req, max_steps=K + W + 1)
+        loop.capture()
+        for _ in range(W):
+            loop.step()
+        torch.cuda.synchronize()
+    finally:
+        parallel_state._TP_SIZE, parallel_state._TP_RANK, parallel_state._TP_COMM = saved
+    dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(K):
+        loop.step()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": world * B * K / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / K, "scaling": "weak",
+            "global_batch": world * B, "parallelism": f"dp{world}", "note": "independent replicas, no collective"}
 
 
 def finish(world: int) -> None:
