@@ -11,12 +11,16 @@
 //   warp 1      tensor-core issuer + TMEM owner:  S_j = Q K_j^T  (A, B from shared memory, K-major) and
 //               O_j = P_j V_j  (A = P_j read from TENSOR MEMORY, B = V_j from shared memory, MN-major descriptor:
 //               V stays [keys][d] exactly as TMA wrote it) -- 16 tcgen05.mma of 128x128x16 per tile
-//   warps 2-5   softmax: thread = query row = TMEM lane, so row max / row sum need no shuffles.  Per tile: read
-//               S_j from TMEM, online softmax in the log2 domain (fp32), write P_j (rounded to the activation dtype,
-//               flashattention2_nopad.py:156) back into the columns S_j occupied, then fold the previous tile's
-//               O_{j-1} (read from TMEM) into the fp32 output row kept in registers:  O = O * alpha_{j-1} + O_{j-1}.
-// TMEM map (512 columns): S0 | S1 | O0 | O1, each 128 fp32 columns; P_j aliases the first 64 columns of S_j.
-// S and O are double buffered, so the tensor core computes S_{j+1} while the softmax warps work on S_j.
+//   warps 2-5   softmax: thread = query row = TMEM lane, so row max / row sum need no shuffles.  Per tile: ONE read of
+//               the whole score row S_j from TMEM into registers, softmax in the log2 domain (fp32), P_j (rounded to
+//               the activation dtype, flashattention2_nopad.py:156) written back over the columns S_j occupied.
+//               The output accumulates IN TENSOR MEMORY across tiles (O += P_j V_j); the running maximum used for
+//               scaling is only raised when a tile exceeds it by more than 2^8 ("lazy rescale"), and only then is the
+//               O row read, multiplied and written back -- exact, because numerator and denominator share one scale.
+//               (v1 read S twice and folded every tile's O through registers: 16 exposed TMEM round trips per tile with
+//               one warp per scheduler; ~7700 cycles per tile against 1024 of tensor-core time.)
+// TMEM map (512 columns): S0 | S1 | O, each 128 fp32 columns; P_j aliases the first 64 columns of S_j.
+// S is double buffered, so the tensor core computes S_{j+1} while the softmax warps work on S_j.
 // Causality: only tiles up to the diagonal are loaded; only the diagonal tile is masked.
 #include "common.cuh"
 #include "tma_desc.cuh"
@@ -35,7 +39,7 @@ struct __align__(8) Ctl {
   uint64_t q_full;
   uint64_t k_full[kStages], k_empty[kStages];
   uint64_t v_full[kStages], v_empty[kStages];
-  uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint64_t s_full[2], p_full[2], o_full;
   uint32_t tmem_base;
 };
 static_assert(sizeof(Ctl) <= 1024, "control block too large");
@@ -64,6 +68,17 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_st_() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -111,8 +126,8 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->s_full[s], 1); mbar_init(&ctl->p_full[s], 4);
-      mbar_init(&ctl->o_full[s], 1); mbar_init(&ctl->o_empty[s], 4);
     }
+    mbar_init(&ctl->o_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -183,16 +198,16 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       tc_fence_after();
       if (elect_one()) {
         const uint32_t v_addr = smem_u32(v_ring + st * kTileBytes);
-        const uint32_t d = tmem_base + 256u + (uint32_t)(j & 1) * 128u;
+        const uint32_t d = tmem_base + 256u;                           // the output accumulates across tiles
         const uint32_t a = tmem_base + (uint32_t)(j & 1) * 128u;       // P_j: 64 columns of packed pairs
 #pragma unroll
         for (int kk = 0; kk < kBN / 16; ++kk) {
           // 16 keys per step = two 8-row groups of 1024 B; the d 64..127 half is one LBO (16 KiB) away
           const uint64_t v_desc = umma_desc_sw128_mnmajor(v_addr + kk * 2048, kHalfBytes, 1024);
-          umma_ts(d, a + kk * 8, v_desc, idesc_o, kk ? 1u : 0u);
+          umma_ts(d, a + kk * 8, v_desc, idesc_o, (j | kk) ? 1u : 0u);
         }
         tc_commit(&ctl->v_empty[st]);
-        tc_commit(&ctl->o_full[j & 1]);
+        tc_commit(&ctl->o_full);
       }
       __syncwarp();
     };
@@ -201,8 +216,8 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
       if (j + 1 < ntiles) issue_s(j + 1);        // the tensor core works on S_{j+1} while the softmax warps are on S_j
+      // P_j is in place and -- the softmax warps arrive only after any rescale of O -- the output may be added to
       mbar_wait(&ctl->p_full[j & 1], (uint32_t)(j >> 1) & 1u);
-      mbar_wait(&ctl->o_empty[j & 1], ((uint32_t)(j >> 1) & 1u) ^ 1u);
       tc_fence_after();
       issue_pv(j);
     }
@@ -212,27 +227,8 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     const int row = quad * 32 + lane;
     const int64_t qpos = q0 + row;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float o_acc[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-
-    auto fold_o = [&](int j, float alpha) {
-      mbar_wait(&ctl->o_full[j & 1], (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t ob = lane_base + 256u + (uint32_t)(j & 1) * 128u;
-#pragma unroll
-      for (int c = 0; c < kD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ob + c, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->o_empty[j & 1]);
-    };
+    float m_used = -INFINITY, l_run = 0.f;      // m_used: the maximum the accumulated P / O / l are scaled by
+    constexpr float kLazy = 8.0f;               // log2 units: rescale only when a tile exceeds m_used by 2^8
 
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&ctl->s_full[j & 1], (uint32_t)(j >> 1) & 1u);
@@ -240,64 +236,85 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       const uint32_t sb = lane_base + (uint32_t)(j & 1) * 128u;
       const bool diag = (int64_t)(j + 1) * kBN > q0;             // only the last tile reaches past some query row
       const int64_t key0 = (int64_t)j * kBN;
-      // pass 1: row maximum
+      // the whole score row in one round trip
+      uint32_t sv[kBN];
+#pragma unroll
+      for (int c = 0; c < kBN; c += 32) tmem_ld_32x32b_x32(sb + c, *reinterpret_cast<uint32_t(*)[32]>(sv + c));
+      tc_wait_ld();
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < kBN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(sb + c, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]);
-          const bool vis = !diag || key0 + c + i <= qpos;
-          mx = vis ? fmaxf(mx, s) : mx;
-        }
+      for (int i = 0; i < kBN; ++i) {
+        const bool vis = !diag || key0 + i <= qpos;
+        mx = vis ? fmaxf(mx, __uint_as_float(sv[i])) : mx;
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_tile = mx * p.scale_log2;
+      const bool grow = m_tile > m_used + kLazy;                 // first tile: m_used = -inf -> true
+      const float m_new = grow ? m_tile : m_used;
       const float base = m_new == -INFINITY ? 0.f : m_new;       // fully masked (padding) rows: avoid inf - inf
-      const float alpha = fast_exp2(m_run - base);
-      // pass 2: probabilities, row sum, P_j -> TMEM (over the columns S_j's first half occupied)
+      const float alpha = grow ? fast_exp2(m_used - base) : 1.0f;
       float lsum = 0.f;
 #pragma unroll
       for (int c = 0; c < kBN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(sb + c, v);
-        tc_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const bool vis0 = !diag || key0 + c + i <= qpos;
           const bool vis1 = !diag || key0 + c + i + 1 <= qpos;
-          const float p0 = vis0 ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -base)) : 0.f;
-          const float p1 = vis1 ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -base)) : 0.f;
+          const float p0 = vis0 ? fast_exp2(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, -base)) : 0.f;
+          const float p1 = vis1 ? fast_exp2(fmaf(__uint_as_float(sv[c + i + 1]), p.scale_log2, -base)) : 0.f;
           lsum += p0 + p1;
           pk[i >> 1] = pack2<T>(p0, p1);
         }
         tmem_st_32x32b_x16(sb + (c >> 1), pk);
       }
+      l_run = l_run * alpha + lsum;
+      m_used = m_new;
+      if (j > 0) {
+        // every softmax warp follows EVERY phase of o_full (no skipped phases, no parity aliasing); by now PV_{j-1}
+        // has long retired, so this wait is free in the common case
+        mbar_wait(&ctl->o_full, (uint32_t)(j - 1) & 1u);
+        if (__any_sync(0xffffffffu, grow)) {
+          tc_fence_after();
+          const uint32_t ob = lane_base + 256u;
+#pragma unroll
+          for (int c = 0; c < kD; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(ob + c, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(ob + c, v);
+          }
+        }
+      }
       tc_wait_st_();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->p_full[j & 1]);
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      if (j > 0) fold_o(j - 1, alpha_prev);
-      alpha_prev = alpha;
     }
-    fold_o(ntiles - 1, alpha_prev);
-
-    if (qpos < seq_len) {
+    // the last PV, then the normalised row goes out
+    mbar_wait(&ctl->o_full, (uint32_t)(ntiles - 1) & 1u);
+    tc_fence_after();
+    const bool row_ok = qpos < seq_len;
+    {
       const float inv = 1.0f / l_run;
-      T* orow = reinterpret_cast<T*>(p.out) + (seq_start + qpos) * p.o_ts + (int64_t)head * p.o_hs;
+      T* orow = reinterpret_cast<T*>(p.out) + (seq_start + (row_ok ? qpos : 0)) * p.o_ts + (int64_t)head * p.o_hs;
 #pragma unroll
-      for (int c = 0; c < kD; c += 8) {
-        uint4 w;
-        w.x = pack2<T>(o_acc[c] * inv, o_acc[c + 1] * inv);
-        w.y = pack2<T>(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-        w.z = pack2<T>(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
-        w.w = pack2<T>(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + c) = w;
+      for (int c = 0; c < kD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_base + 256u + c, v);          // warp-collective: outside the row predicate
+        tc_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack2<T>(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+            w.y = pack2<T>(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+            w.z = pack2<T>(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+            w.w = pack2<T>(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c + i) = w;
+          }
+        }
       }
     }
   }

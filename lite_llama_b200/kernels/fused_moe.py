@@ -50,12 +50,16 @@ def _quant_kind(weight: torch.Tensor, scale: torch.Tensor | None) -> int:
     raise ValueError(f"quantised expert weights must be uint8 or int8, got {weight.dtype}")
 
 
-def _block_size(num_tokens: int) -> int:
-    """Row-block of the grouped GEMM (= UMMA N): 16 / 32 / 64 by token count, the reference's
-    BLOCK_M thresholds (fused_moe.py:214-222)."""
-    if num_tokens <= 16:
+def _block_size(num_tokens: int, top_k: int = 1, num_experts: int = 1) -> int:
+    """Row-block of the grouped GEMM (= UMMA N): 16 / 32 / 64. The reference picks BLOCK_M from the token count
+    alone (fused_moe.py:214-222); what a block holds is one expert's slots, so the choice here follows the expected
+    slots per expert (tokens * top_k / experts): 32 decode tokens over 128 experts are ~2 slots per expert, and a
+    16-row block halves the padded rows and lets two CTAs share an SM (csrc/moe_gemm.cu). The result does not
+    depend on the block size (every slot is the same dot product)."""
+    per_expert = num_tokens * top_k / max(1, num_experts)
+    if num_tokens <= 16 or per_expert <= 8:
         return 16
-    if num_tokens <= 64:
+    if num_tokens <= 64 or per_expert <= 24:
         return 32
     return 64
 
@@ -120,7 +124,7 @@ def fused_moe(
         raise ValueError("fp16 expert weights must match the activation dtype")
     x = hidden_states if hidden_states.stride(-1) == 1 and hidden_states.stride(0) % 8 == 0 else hidden_states.contiguous()
     flat_weights = topk_weights.reshape(-1).to(dtype).contiguous()
-    block = _block_size(num_tokens)
+    block = _block_size(num_tokens, top_k, num_experts)
     sorted_ids, expert_ids, num_post = moe_align_block_size(topk_ids, block, num_experts)
 
     gate_up = torch.empty((num_tokens * top_k, two_inter), device=device, dtype=dtype)

@@ -955,7 +955,10 @@ def test_bs1_llama_geometry_every_op_of_the_layer():
     act = K().w4a16_matmul_packed(xin, K().w4a16_pack(interleave_gate_up(qg), interleave_gate_up(sg), interleave_gate_up(zg),
                                                       group_size=128), swiglu=True)
     gu = K().w4a16_matmul(xin, qg, sg, zg, group_size=128)
-    assert torch.equal(act, K().swiglu_forward(gu[:, :inter], gu[:, inter:]))
+    # same arithmetic; interleaving moves rows to other tiles, so stream-K cuts their K range at other raw blocks and
+    # the fp32 partial sums are grouped differently: equal up to the last fp16 bit, not bit for bit (the bit-exact
+    # comparison on unshared tiles is test_w4a16_swiglu_epilogue_is_bit_identical_to_gemm_then_swiglu)
+    close(act.cpu(), K().swiglu_forward(gu[:, :inter], gu[:, inter:]).cpu(), rtol=2e-3, atol=1e-4)
     # lm_head: the full 128256 x 4096 fp16 matrix at M = 1
     lm = torch.randn(V, h, device=dev, dtype=torch.float16) * 0.02
     logits = K().linear(xin, lm)
