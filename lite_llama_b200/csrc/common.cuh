@@ -479,6 +479,22 @@ static inline void b2l_hang_arm(cudaStream_t st) {
   armed[dev] = true;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember the largest value set per device
+// (a process that drives several GPUs must set it on each; round-1 ADVICE).  `cache` is a function-local static array.
+template <typename Kern>
+static inline cudaError_t b2l_ensure_dynamic_smem(Kern kern, int bytes, int (&cache)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev &= 63;
+  if (bytes > cache[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    cache[dev] = bytes;
+  }
+  return cudaSuccess;
+}
+
 // Host side: launch `kern` on `st`, with the PDL attribute unless the library switch is off.
 template <typename... KArgs, typename... Args>
 static inline cudaError_t b2l_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

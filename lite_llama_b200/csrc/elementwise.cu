@@ -97,23 +97,31 @@ __global__ void __launch_bounds__(256) skip_rmsnorm_block_kernel(T* __restrict__
 
 // Generic fallback without a residual: any n, one warp per row, two passes over x.
 template <typename T>
-__global__ void skip_rmsnorm_warp_kernel(T* __restrict__ y, const T* __restrict__ x, const T* __restrict__ w,
-                                         int64_t rows, int64_t n, int64_t x_stride, int64_t y_stride, float eps) {
+__global__ void skip_rmsnorm_warp_kernel(T* __restrict__ y, const T* __restrict__ x, T* __restrict__ res,
+                                         const T* __restrict__ w, int64_t rows, int64_t n, int64_t x_stride,
+                                         int64_t r_stride, int64_t y_stride, float eps) {
   pdl_prologue();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const T* xr = x + row * x_stride;
+  T* rr = res ? res + row * r_stride : nullptr;
   T* yr = y + row * y_stride;
+  // pass 1 only reads: the residual is overwritten in pass 2, where x + residual is formed again (same fp32 sum)
   float ss = 0.f;
   for (int64_t c = lane; c < n; c += 32) {
-    const float s = to_f32(xr[c]);
+    const float s = to_f32(xr[c]) + (rr ? to_f32(rr[c]) : 0.f);
     ss += s * s;
   }
   ss = warp_reduce_sum(ss);
   const float rrms = div_full(1.0f, sqrt_approx(ss / (float)n + eps));
   for (int64_t c = lane; c < n; c += 32) {
-    T nrm = from_f32<T>(to_f32(xr[c]) * rrms);
+    float s = to_f32(xr[c]);
+    if (rr) {
+      s += to_f32(rr[c]);
+      rr[c] = from_f32<T>(s);
+    }
+    T nrm = from_f32<T>(s * rrms);
     yr[c] = from_f32<T>(to_f32(nrm) * to_f32(w[c]));
   }
 }
@@ -195,11 +203,9 @@ static int launch_skip_rmsnorm(void* y, const void* x, void* res, const void* w,
   else if (n <= 32 * 128)
     b2l_launch(skip_rmsnorm_warp_reg_kernel<T, 128>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (T*)res, (const T*)w, rows,
                                                                    n, xs, rs, ys, eps);
-  else {
-    B2L_REQUIRE(res == nullptr, "skip_rmsnorm: unaligned rows wider than 4096 with a residual are unsupported (n=%lld)",
-                (long long)n);
-    b2l_launch(skip_rmsnorm_warp_kernel<T>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (const T*)w, rows, n, xs, ys, eps);
-  }
+  else  // any width / alignment, with or without a residual: one warp per row, two passes
+    b2l_launch(skip_rmsnorm_warp_kernel<T>, dim3(grid), dim3(warps * 32), (size_t)(0), st, (T*)y, (const T*)x, (T*)res,
+               (const T*)w, rows, n, xs, rs, ys, eps);
   B2L_LAUNCH_CHECK();
   return B2L_OK;
 }
@@ -628,26 +634,28 @@ extern "C" int b2l_quantize_activations_int8(void* q, void* scales, const void* 
 //   out[m, :] = sum_k in[m*top_k + k, :]   (fp32 accumulate, in slot order)
 // --------------------------------------------------------------------------- //
 template <typename T>
-__global__ void moe_sum_kernel(T* __restrict__ out, const T* __restrict__ in, int64_t n, int top_k) {
+__global__ void moe_sum_kernel(T* __restrict__ out, const T* __restrict__ in, int64_t tokens, int64_t n, int top_k) {
   pdl_prologue();
-  const int64_t m = blockIdx.y;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    const T* base = in + m * top_k * n + c;
-    for (int i = 0; i < top_k; ++i) acc += to_f32(base[(int64_t)i * n]);
-    out[m * n + c] = from_f32<T>(acc);
+  // grid.y is capped at 65535: tokens are swept with a grid stride (MoE prefill can exceed the cap)
+  for (int64_t m = blockIdx.y; m < tokens; m += gridDim.y) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      const T* base = in + m * top_k * n + c;
+      for (int i = 0; i < top_k; ++i) acc += to_f32(base[(int64_t)i * n]);
+      out[m * n + c] = from_f32<T>(acc);
+    }
   }
 }
 
 extern "C" int b2l_moe_sum(void* out, const void* in, int64_t tokens, int64_t n, int top_k, int dtype, void* stream) {
   B2L_REQUIRE(out && in, "moe_sum: null pointer");
   if (tokens == 0 || n == 0) return B2L_OK;
-  dim3 grid((unsigned)cdiv64(n, 256), (unsigned)tokens);
+  dim3 grid((unsigned)cdiv64(n, 256), (unsigned)(tokens > 65535 ? 65535 : tokens));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2L_F16)
-    b2l_launch(moe_sum_kernel<__half>, dim3(grid), dim3(256), (size_t)(0), st, (__half*)out, (const __half*)in, n, top_k);
+    b2l_launch(moe_sum_kernel<__half>, dim3(grid), dim3(256), (size_t)(0), st, (__half*)out, (const __half*)in, tokens, n, top_k);
   else if (dtype == B2L_BF16)
-    b2l_launch(moe_sum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), st, (__nv_bfloat16*)out, (const __nv_bfloat16*)in, n, top_k);
+    b2l_launch(moe_sum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), st, (__nv_bfloat16*)out, (const __nv_bfloat16*)in, tokens, n, top_k);
   else
     B2L_UNSUPPORTED("moe_sum: dtype %d", dtype);
   B2L_LAUNCH_CHECK();

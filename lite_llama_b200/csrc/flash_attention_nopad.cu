@@ -229,11 +229,8 @@ __global__ void __launch_bounds__(kThreads) flash_prefill_kernel(const PrefillPa
 template <typename T, int D>
 int launch_prefill(const PrefillParams& p, int64_t batch, int64_t max_len, cudaStream_t st) {
   constexpr int smem = smem_bytes<D>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2L_CUDA_CHECK(cudaFuncSetAttribute(flash_prefill_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static int configured[64] = {0};
+  B2L_CUDA_CHECK(b2l_ensure_dynamic_smem(flash_prefill_kernel<T, D>, smem, configured));
   dim3 grid((unsigned)cdiv64(max_len, kBM), (unsigned)p.Hq, (unsigned)batch);
   b2l_launch(flash_prefill_kernel<T, D>, dim3(grid), dim3(kThreads), (size_t)(smem), st, p);
   B2L_LAUNCH_CHECK();

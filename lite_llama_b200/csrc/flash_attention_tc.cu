@@ -230,22 +230,26 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     float m_used = -INFINITY, l_run = 0.f;      // m_used: the maximum the accumulated P / O / l are scaled by
     constexpr float kLazy = 8.0f;               // log2 units: rescale only when a tile exceeds m_used by 2^8
 
-    for (int j = 0; j < ntiles; ++j) {
+    auto tile = [&](const int j, auto masked) {
+      constexpr bool kMasked = decltype(masked)::value;
       mbar_wait(&ctl->s_full[j & 1], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const uint32_t sb = lane_base + (uint32_t)(j & 1) * 128u;
-      const bool diag = (int64_t)(j + 1) * kBN > q0;             // only the last tile reaches past some query row
       const int64_t key0 = (int64_t)j * kBN;
       // the whole score row in one round trip
       uint32_t sv[kBN];
 #pragma unroll
       for (int c = 0; c < kBN; c += 32) tmem_ld_32x32b_x32(sb + c, *reinterpret_cast<uint32_t(*)[32]>(sv + c));
       tc_wait_ld();
+      // causal mask of the diagonal tile as a per-thread column limit; branch-free selects (the first version's
+      // 64-bit predicates compiled into ~600 integer compares and a branch around every exp2 per tile)
+      const int limit = (int)(qpos - key0);                      // masked tile: key column i is visible iff i <= limit
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < kBN; ++i) {
-        const bool vis = !diag || key0 + i <= qpos;
-        mx = vis ? fmaxf(mx, __uint_as_float(sv[i])) : mx;
+        float v = __uint_as_float(sv[i]);
+        if (kMasked) v = i <= limit ? v : -INFINITY;
+        mx = fmaxf(mx, v);
       }
       const float m_tile = mx * p.scale_log2;
       const bool grow = m_tile > m_used + kLazy;                 // first tile: m_used = -inf -> true
@@ -253,19 +257,23 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       const float base = m_new == -INFINITY ? 0.f : m_new;       // fully masked (padding) rows: avoid inf - inf
       const float alpha = grow ? fast_exp2(m_used - base) : 1.0f;
       float lsum = 0.f;
+      {
 #pragma unroll
-      for (int c = 0; c < kBN; c += 32) {
-        uint32_t pk[16];
+        for (int c = 0; c < kBN; c += 32) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const bool vis0 = !diag || key0 + c + i <= qpos;
-          const bool vis1 = !diag || key0 + c + i + 1 <= qpos;
-          const float p0 = vis0 ? fast_exp2(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, -base)) : 0.f;
-          const float p1 = vis1 ? fast_exp2(fmaf(__uint_as_float(sv[c + i + 1]), p.scale_log2, -base)) : 0.f;
-          lsum += p0 + p1;
-          pk[i >> 1] = pack2<T>(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, -base));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + i + 1]), p.scale_log2, -base));
+            if (kMasked) {                                         // selects, not branches around the exp2
+              p0 = c + i <= limit ? p0 : 0.f;
+              p1 = c + i + 1 <= limit ? p1 : 0.f;
+            }
+            lsum += p0 + p1;
+            pk[i >> 1] = pack2<T>(p0, p1);
+          }
+          tmem_st_32x32b_x16(sb + (c >> 1), pk);
         }
-        tmem_st_32x32b_x16(sb + (c >> 1), pk);
       }
       l_run = l_run * alpha + lsum;
       m_used = m_new;
@@ -291,7 +299,10 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->p_full[j & 1]);
-    }
+    };
+    // only the LAST tile of a query block touches the diagonal: every other tile runs the copy without mask code
+    for (int j = 0; j + 1 < ntiles; ++j) tile(j, std::false_type{});
+    tile(ntiles - 1, std::true_type{});
     // the last PV, then the normalised row goes out
     mbar_wait(&ctl->o_full, (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
@@ -430,7 +441,7 @@ fa_tc_one_tile_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
     float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < kBN; ++i) mx = i <= row ? fmaxf(mx, s[i]) : mx;      // causal: key i visible iff i <= row
+    for (int i = 0; i < kBN; ++i) mx = fmaxf(mx, i <= row ? s[i] : -INFINITY);   // causal: key i visible iff i <= row
     const float base = mx * p.scale_log2;
     float lsum = 0.f;
 #pragma unroll
@@ -438,8 +449,10 @@ fa_tc_one_tile_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float p0 = (c + i <= row) ? fast_exp2(fmaf(s[c + i], p.scale_log2, -base)) : 0.f;
-        const float p1 = (c + i + 1 <= row) ? fast_exp2(fmaf(s[c + i + 1], p.scale_log2, -base)) : 0.f;
+        float p0 = fast_exp2(fmaf(s[c + i], p.scale_log2, -base));          // selects, not branches around the exp2
+        float p1 = fast_exp2(fmaf(s[c + i + 1], p.scale_log2, -base));
+        p0 = (c + i <= row) ? p0 : 0.f;
+        p1 = (c + i + 1 <= row) ? p1 : 0.f;
         lsum += p0 + p1;
         pk[i >> 1] = pack2<T>(p0, p1);
       }

@@ -357,11 +357,8 @@ Plan make_plan(int64_t batch, int Hq, int Hkv, int D, int64_t max_len) {
 
 template <typename T, int D>
 int launch_decode(const DecodeParams& p, const Plan& pl, int64_t batch, cudaStream_t st) {
-  static int configured = 0;
-  if (pl.smem > configured) {
-    B2L_CUDA_CHECK(cudaFuncSetAttribute(flash_decode_split_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-    configured = pl.smem;
-  }
+  static int configured[64] = {0};
+  B2L_CUDA_CHECK(b2l_ensure_dynamic_smem(flash_decode_split_kernel<T, D>, pl.smem, configured));
   dim3 grid((unsigned)p.splits, (unsigned)(p.Hkv / p.HB), (unsigned)batch);
   const int threads = (p.HB * p.qblocks + 1) * 32;
   b2l_launch(flash_decode_split_kernel<T, D>, dim3(grid), dim3(threads), (size_t)(pl.smem), st, p);

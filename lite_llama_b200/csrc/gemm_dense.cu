@@ -210,11 +210,8 @@ template <int KIND, typename T, int BT>
 static int launch_bt(const CUtensorMap& tw, const CUtensorMap& tx, const DenseParams& p, const SplitPlan& pl,
                      cudaStream_t st) {
   auto kern = gemm_swapab_kernel<KIND, T, BT>;
-  static int configured_smem = 0;
-  if (pl.smem_bytes > configured_smem) {
-    B2L_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    configured_smem = pl.smem_bytes;
-  }
+  static int configured_smem[64] = {0};
+  B2L_CUDA_CHECK(b2l_ensure_dynamic_smem(kern, pl.smem_bytes, configured_smem));
   dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.m_tiles, (unsigned)pl.splits);
   b2l_launch(kern, dim3(grid), dim3(192), (size_t)(pl.smem_bytes), st, tw, tx, p);
   B2L_LAUNCH_CHECK();

@@ -1245,11 +1245,8 @@ template <int QK, int BT, bool DBG, int LAYOUT, int EPI = 0>
 static int launch_q_inst(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
                          cudaStream_t st) {
   auto kern = gemm_quant_kernel<QK, BT, DBG, LAYOUT, EPI>;
-  static int configured_smem = 0;
-  if (pl.smem_bytes > configured_smem) {
-    B2L_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    configured_smem = pl.smem_bytes;
-  }
+  static int configured_smem[64] = {0};
+  B2L_CUDA_CHECK(b2l_ensure_dynamic_smem(kern, pl.smem_bytes, configured_smem));
   dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.m_tiles, (unsigned)pl.splits);
   if (pl.sk_ctas > 0) grid = dim3((unsigned)pl.sk_ctas, (unsigned)pl.m_tiles, 1);
   b2l_launch(kern, dim3(grid), dim3(kQuantThreads), (size_t)(pl.smem_bytes), st, tw, tx, p);

@@ -361,11 +361,8 @@ template <int MK, int BT>
 static int launch_moe(const CUtensorMap& tw, const MoeParams& p, const MoePlan& pl, int n_tiles, int max_blocks,
                       cudaStream_t st) {
   auto kern = moe_gemm_kernel<MK, BT>;
-  static int configured = 0;
-  if (pl.smem > configured) {
-    B2L_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-    configured = pl.smem;
-  }
+  static int configured[64] = {0};
+  B2L_CUDA_CHECK(b2l_ensure_dynamic_smem(kern, pl.smem, configured));
   dim3 grid((unsigned)n_tiles, (unsigned)max_blocks);
   b2l_launch(kern, dim3(grid), dim3(kMoeThreads), (size_t)(pl.smem), st, tw, p);
   B2L_LAUNCH_CHECK();

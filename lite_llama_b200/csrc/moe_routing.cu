@@ -34,7 +34,7 @@ moe_align_kernel(const void* __restrict__ topk_ids, int id_width, int num_slots,
   const int c1 = c0 + chunk < num_slots ? c0 + chunk : num_slots;
   for (int i = c0 + lane; i < c1; i += 32) {
     const int e = (int)load_index(topk_ids, i, id_width);
-    atomicAdd(&hist[warp * num_experts + e], 1);
+    if (e >= 0 && e < num_experts) atomicAdd(&hist[warp * num_experts + e], 1);   // ids outside [0, E) are dropped
   }
   __syncthreads();
   // per expert: total count, and turn hist[w][e] into the exclusive prefix over warps
@@ -63,8 +63,9 @@ moe_align_kernel(const void* __restrict__ topk_ids, int id_width, int num_slots,
   // stable placement: 32 slots at a time, rank inside the group by match_any
   for (int base = c0; base < c1; base += 32) {
     const int i = base + lane;
-    const bool valid = i < c1;
-    const int e = valid ? (int)load_index(topk_ids, i, id_width) : -1 - lane;   // unique dummy keys
+    bool valid = i < c1;
+    int e = valid ? (int)load_index(topk_ids, i, id_width) : -1 - lane;         // unique dummy keys
+    if (valid && (e < 0 || e >= num_experts)) { valid = false; e = -64 - lane; } // out-of-range id: no slot, no smem access
     const unsigned same = __match_any_sync(0xffffffffu, e);
     const int rank = __popc(same & ((1u << lane) - 1u));
     if (valid) {
@@ -153,11 +154,8 @@ extern "C" int b2l_moe_align_block_size(const void* topk_ids, int id_width, int6
   const int max_blocks = (max_padded + block_size - 1) / block_size;
   const int smem = (kAlignWarps + 2) * num_experts * (int)sizeof(int);
   B2L_REQUIRE(smem <= 200 * 1024, "moe_align_block_size: too many experts for one CTA");
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    B2L_CUDA_CHECK(cudaFuncSetAttribute(moe_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static int configured[64] = {0};
+  if (smem > 48 * 1024) B2L_CUDA_CHECK(b2l_ensure_dynamic_smem(moe_align_kernel, smem, configured));
   b2l_launch(moe_align_kernel, dim3(1), dim3(kAlignThreads), (size_t)(smem), (cudaStream_t)stream, 
       topk_ids, id_width, (int)num_slots, block_size, num_experts, (int32_t*)sorted_token_ids, (int32_t*)expert_ids,
       (int32_t*)num_tokens_post_padded, max_padded, max_blocks);

@@ -69,6 +69,18 @@ def test_skip_rmsnorm_matches_oracle(shape, dtype):
     assert x_back.data_ptr() == x.data_ptr()
 
 
+def test_skip_rmsnorm_wide_unaligned_rows_with_residual():
+    """Rows wider than 4096 whose length is not a multiple of 8 take the two-pass warp kernel, residual included
+    (round-1 ADVICE: that combination used to be rejected)."""
+    x = torch.randn(3, 4100 + 3, device="cuda", dtype=torch.float16)
+    res = torch.randn_like(x)
+    w = torch.randn(x.shape[-1], device="cuda", dtype=torch.float16)
+    y, r = K().skip_rmsnorm(x, res.clone(), w, 1e-5)
+    yr, rr = ops.skip_rmsnorm(x.cpu(), res.cpu(), w.cpu(), 1e-5)
+    close(y.cpu(), yr, rtol=2e-3, atol=2e-3)
+    close(r.cpu(), rr, rtol=1e-3, atol=1e-3)
+
+
 def test_skip_rmsnorm_per_head_layout():
     # the Qwen3 q/k-norm call: [tokens, heads, head_dim] normalised over head_dim (models/base.py:222-225)
     x = torch.randn(7, 14, 128, device="cuda", dtype=torch.float16)
