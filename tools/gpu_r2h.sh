@@ -8,6 +8,8 @@ run() { local name=$1 t=$2; shift 2
   echo "$name exit=$?" >> $S; }
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ "$N" = "2" ]; then
+  run quick 120 python -m pytest -q -p no:cacheprovider -x --timeout 40 tests/test_kernels_gpu.py tests/test_host_gpu.py -m gpu -k "flash_attention or rmsnorm or moe or llama3 or bs1"
+  run triton_fa 200 python tools/bench_triton_ref.py --only flash_attention --out gpurun_out/r2h_triton_fa
   run tp_check 300 $TR --master-port 29541 tools/tp_check.py
   run tp_test 400 python -m pytest -q -p no:cacheprovider -x tests/test_tp_gpu.py -m gpu
 fi
@@ -17,7 +19,9 @@ if [ "$N" != "8" ]; then
   run bench_moe_tp 500 $TR --master-port 29546 bench.py --gpus $N --model qwen3-30b-a3b --quant fp8 --steps 32 --warmup 4 --no-dp-line --watchdog-s 450
 fi
 cat $S
-for f in tp_check tp_test bench_tp bench_ref bench_moe_tp; do
+for f in quick tp_check tp_test bench_tp bench_ref bench_moe_tp; do
   [ -f gpurun_out/r2h_n${N}_$f.out ] || continue
   echo "== $f"; grep "^{" gpurun_out/r2h_n${N}_$f.out | cut -c1-2200; tail -4 gpurun_out/r2h_n${N}_$f.out | grep -v "^{" | cut -c1-300; grep -v "^\[W\|^W1\|frame #\|OMP_NUM\|\*\*\*\*" gpurun_out/r2h_n${N}_$f.err | tail -6 | cut -c1-300
 done
+
+[ -f gpurun_out/r2h_triton_fa.md ] && cat gpurun_out/r2h_triton_fa.md

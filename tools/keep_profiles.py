@@ -29,7 +29,8 @@ OURS = ["gemm_quant_kernel", "gemm_swapab_kernel", "moe_gemm_kernel", "flash_dec
         "flash_decode_combine_kernel", "flash_prefill_kernel", "skip_rmsnorm_block_kernel", "skip_rmsnorm_warp_reg_kernel",
         "skip_rmsnorm_warp_kernel", "rope_kernel", "rope_kv_kernel", "swiglu_kernel", "update_kv_buffer_kernel",
         "update_kv_index_kernel", "quantize_act_int8_kernel", "moe_sum_kernel", "moe_align_kernel", "moe_route_kernel",
-        "argmax_rows_kernel", "embed_rope_gather_kernel"]
+        "argmax_rows_kernel", "embed_rope_gather_kernel", "rope_kv_write_kernel", "fa_tc_kernel", "fa_tc_one_tile_kernel",
+        "tp_allreduce_rmsnorm_kernel"]
 
 
 def kname(full: str) -> str:
@@ -56,7 +57,7 @@ def launches(prefix: str) -> None:
     # decode step = launches between two consecutive lm_head GEMMs; take the last window that looks like a full step
     window = None
     for a, b in zip(reversed(heads[:-1]), reversed(heads[1:])):
-        if b - a >= 100 and sum(1 for s in seq[a + 1:b + 1] if "flash_decode_split" in s[0]) > 0:
+        if b - a >= 40 and sum(1 for s in seq[a + 1:b + 1] if "flash_decode_split" in s[0]) > 0:
             window = (a + 1, b + 1)
             break
     lines = [f"# source: gpurun_out/launches.csv ({len(seq)} launches in the whole bench.py run)"]
