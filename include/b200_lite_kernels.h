@@ -130,6 +130,11 @@ int b2l_rope_kv_write(void* q, void* k, const void* v, const void* cos, const vo
                       int64_t k_head_stride, int64_t v_tok_stride, int64_t v_head_stride, int64_t cs_batch_stride,
                       int64_t cs_seq_stride, int64_t d_tok_stride, int64_t d_head_stride, int dtype, void* stream);
 
+/* Greedy sampling: out[r] = argmax_j x[r, j] (int64; ties -> lowest index).  Reference: temperature-0 path of the
+ * Sampler, torch.argmax over the [batch, vocab] logits (lite_llama/engine/sampler.py, engine/llm_engine.py:172). */
+int b2l_argmax_rows(void* out_index_i64, const void* x, int64_t rows, int64_t n, int64_t row_stride, int dtype,
+                    void* stream);
+
 /* Dense projection y = x @ w.T (+ bias): the reference's F.linear call sites
  * (lite_llama/models/quantization/methods/unquantized.py:21-22, lite_llama/models/base.py:489). */
 int64_t b2l_linear_workspace_bytes(int64_t m, int64_t n, int64_t k, int elem_bytes);

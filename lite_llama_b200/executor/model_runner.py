@@ -20,7 +20,7 @@ from typing import Any
 import torch
 
 from ..distributed import all_reduce_min, divide, get_tp_world_size
-from ..kernels import update_kv_index
+from ..kernels import argmax_rows, update_kv_index
 from ..kernels._common import counters
 from .attention_metadata import AttentionMetadata
 from .decoder import Decoder, DecoderWeights, random_weights
@@ -118,7 +118,7 @@ class GreedyDecodeLoop:
         # position = b_seq_len - 1, cur_select_index = the rows reserved for it
         update_kv_index(self.info.b_req_tokens_table, self.b_req_idx, self.b_seq_len, self.cur_select_index)
         logits = self.runner.model.forward(self.input_ids, self.position_ids, self.info)
-        torch.argmax(logits[:, -1, :], dim=-1, out=self.next_tokens)
+        argmax_rows(logits[:, -1, :], out=self.next_tokens)            # greedy sampling without torch's 45 us reduce
         self.input_ids.copy_(self.next_tokens.unsqueeze(1))
         self.position_ids.add_(1)
         self.b_seq_len.add_(1)

@@ -10,6 +10,7 @@ from .flashdecoding import flash_decoding
 from .fused_moe import fused_moe, moe_align_block_size, route_topk
 from .linear import linear
 from .rope_emb import rope_emb_forward, rope_emb_inplace, rope_kv_write
+from .sampling import argmax_rows
 from .skip_rmsnorm import skip_rmsnorm
 from .swiglu import swiglu_forward
 from .update_kv_buffer import update_kv_buffer, update_kv_buffer_split
@@ -23,6 +24,7 @@ __all__ = [
     "moe_align_block_size",
     "route_topk",
     "linear",
+    "argmax_rows",
     "rope_emb_forward",
     "rope_emb_inplace",
     "rope_kv_write",

@@ -975,3 +975,15 @@ def test_bs1_llama_geometry_every_op_of_the_layer():
     lm = torch.randn(V, h, device=dev, dtype=torch.float16) * 0.02
     logits = K().linear(xin, lm)
     close(logits.cpu(), (xin.float().cpu() @ lm.float().cpu().T), rtol=2e-3, atol=2e-3)
+
+
+def test_argmax_rows_matches_torch_and_breaks_ties_low():
+    for rows, n, dtype in [(32, 128256, torch.float16), (1, 151936, torch.float16), (3, 1000, torch.bfloat16), (5, 7, torch.float16)]:
+        x = torch.randn(rows, n, device="cuda", dtype=dtype)
+        assert torch.equal(K().argmax_rows(x), x.float().argmax(-1))
+        view = torch.randn(rows, 2, n, device="cuda", dtype=dtype)[:, -1, :]      # strided rows, like logits[:, -1, :]
+        assert torch.equal(K().argmax_rows(view), view.float().argmax(-1))
+    t = torch.zeros(2, 4096, device="cuda", dtype=torch.float16)
+    t[0, 100] = t[0, 3000] = 5.0
+    t[1, 4095] = 1.0
+    assert K().argmax_rows(t).tolist() == [100, 4095]

@@ -14,6 +14,7 @@ from __future__ import annotations
 import json
 import os
 import sys
+import time
 from pathlib import Path
 
 import torch
@@ -178,11 +179,19 @@ def main():
             out["hang"] = _lib.hang_report()
         except Exception:
             pass
-    print(json.dumps(out), flush=True)
     if out["ok"]:
+        # one line per rank, never interleaved: rank 0 prints everybody's result
+        every = [None] * world
+        dist.all_gather_object(every, out)
+        if rank == 0:
+            for o in every:
+                print(json.dumps(o), flush=True)
         dist.barrier()
-        destroy_tensor_parallel()
-        sys.exit(0)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)          # captured graphs still hold NCCL kernels: leave without tearing the group down
+    time.sleep(0.5 * rank)
+    print(json.dumps(out), flush=True)
     os._exit(1)
 
 
