@@ -779,6 +779,38 @@ def test_fused_moe_quantised_experts_qwen3_shape(kind):
     close(out, ref, rtol=5e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("tp,g", [(4, 64), (8, 32)])
+def test_fused_moe_sub_block_tensor_parallel_shard(tp, g):
+    """One rank's expert shard of Qwen3-30B-A3B at TP = 4 / 8: 768 / tp intermediate columns per expert, which cuts the
+    checkpoint's 128 x 128 scale blocks; scales refined to g = gcd(128, 768 / tp) and passed as group_n = group_k = g
+    (the reference refuses these shards, lite_llama/models/linear.py:164-177)."""
+    from lite_llama_b200.quantization.params import quantize_fp8_blockwise, reblock_scales
+
+    tokens, E, top_k, hidden, inter = 32, 16, 4, 2048, 768
+    il = inter // tp
+    x = (torch.randn(tokens, hidden) / hidden**0.5).half()
+    gate = torch.randn(E, inter, hidden) / hidden**0.5
+    up = torch.randn(E, inter, hidden) / hidden**0.5
+    down = torch.randn(E, hidden, inter) / inter**0.5
+    rank = 1
+    lo, hi = rank * il, (rank + 1) * il
+    parts = []
+    for t in (gate, up, down):
+        q, sc = quantize_fp8_blockwise(t)
+        parts.append((q, reblock_scales(reblock_scales(sc, 128, g, 1), 128, g, 2)))
+    (qg, sg), (qu, su), (qd, sd) = parts
+    w1 = torch.cat([qg[:, lo:hi], qu[:, lo:hi]], dim=1).contiguous()
+    s1 = torch.cat([sg[:, lo // g:hi // g], su[:, lo // g:hi // g]], dim=1).contiguous()
+    w2 = qd[:, :, lo:hi].contiguous()
+    s2 = sd[:, :, lo // g:hi // g].contiguous()
+    ids = torch.randint(0, E, (tokens, top_k))
+    tw = torch.softmax(torch.randn(tokens, top_k), dim=-1).half()
+    out = K().fused_moe(x.cuda(), w1.cuda(), w2.cuda(), tw.cuda(), ids.cuda(), w1_scale=s1.cuda(), w2_scale=s2.cuda(),
+                        group_n=g, group_k=g)
+    ref = ops.fused_moe(x, w1, w2, tw, ids, s1, s2, g, g)
+    close(out, ref, rtol=5e-3, atol=1e-3)
+
+
 def test_fused_moe_zero_routing_weight_drops_the_slot():
     hidden, inter, E, top_k = 128, 64, 4, 2
     x = torch.randn(5, hidden).half()

@@ -13,6 +13,9 @@ if [ "$N" = "2" ]; then
   run tp_check 300 $TR --master-port 29541 tools/tp_check.py
   run tp_test 400 python -m pytest -q -p no:cacheprovider -x tests/test_tp_gpu.py -m gpu
 fi
+if [ "$N" = "4" ]; then
+  run quick 120 python -m pytest -q -p no:cacheprovider -x --timeout 40 tests/test_kernels_gpu.py -m gpu -k "fused_moe or argmax or rmsnorm"
+fi
 run bench_tp 400 $TR --master-port 29542 bench.py --gpus $N --steps 64 --warmup 4
 run bench_ref 300 $TR --master-port 29545 bench.py --impl reference --gpus $N --steps 8 --warmup 1
 if [ "$N" != "8" ]; then
