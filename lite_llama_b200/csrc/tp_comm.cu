@@ -26,8 +26,8 @@
 namespace {
 
 constexpr int kMaxWorld = 8;
-constexpr int kThreads = 256;
-constexpr int kMaxIters = 6;                 // packets per thread: rows up to 256 * 6 * 6 = 9216 elements
+constexpr int kThreads = 768;                 // one packet per thread for hidden 4096: every poll of a row is in flight at once
+constexpr int kMaxIters = 2;                 // packets per thread: rows up to 768 * 2 * 6 = 9216 elements
 constexpr int kPktElems = 6;                 // a 16-byte packet = 6 activation values (3 words) + the epoch word
 
 struct CommState {
@@ -143,14 +143,24 @@ __global__ void __launch_bounds__(kThreads) tp_allreduce_rmsnorm_kernel(const Fu
       float acc[kPktElems];
 #pragma unroll
       for (int j = 0; j < kPktElems; ++j) acc[j] = 0.f;
-      for (int r = 0; r < p.world; ++r) {
+      // all peers' packets of this chunk are requested before the first one is examined (the polls are L2 round trips:
+      // one after the other they cost (world - 1) x ~0.7 us per chunk, which is what made the 4-rank exchange 11 us)
+      uint4 pv[kMaxWorld];
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < p.world && r != p.rank)
+          pv[r] = ld_pkt(mine_base + (((int64_t)par * p.world + r) * p.max_rows + row) * p.row_bytes + (int64_t)c * 16);
+      }
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r >= p.world) continue;
         uint32_t w3[3];
         if (r == p.rank) {
           w3[0] = mine[i][0]; w3[1] = mine[i][1]; w3[2] = mine[i][2];
         } else {
-          const unsigned char* src = mine_base + (((int64_t)par * p.world + r) * p.max_rows + row) * p.row_bytes + (int64_t)c * 16;
-          uint4 v = ld_pkt(src);
+          uint4 v = pv[r];
           if (v.w != e) {
+            const unsigned char* src = mine_base + (((int64_t)par * p.world + r) * p.max_rows + row) * p.row_bytes + (int64_t)c * 16;
             const unsigned long long t0 = b2l_globaltimer();
             do {
               v = ld_pkt(src);

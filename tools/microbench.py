@@ -155,6 +155,16 @@ def main():
                 r = bench_gemm(kind, m, 4096, 4096)
                 r["frac_tensor"] = r["tflops"] / tf
                 out.append(r)
+    if args.which in ("all", "prefill_gemm"):
+        # prefill-sized token counts at the Llama-3-8B gate|up shape: our dense and W4A16 kernels beside cuBLAS
+        for m in (1024, 4096):
+            for kind in ("torch", "dense", "w4a16"):
+                try:
+                    r = bench_gemm(kind, m, 28672, 4096)
+                    r["frac_tensor"] = r["tflops"] / tf
+                except Exception as e:
+                    r = {"op": kind, "m": m, "n": 28672, "k": 4096, "error": repr(e)[:200]}
+                out.append(r)
     for r in out:
         r["peaks"] = src
         print(json.dumps(r))
