@@ -13,6 +13,9 @@ if [ "$N" = "2" ]; then
   run tp_check 300 $TR --master-port 29541 tools/tp_check.py
   run tp_test 400 python -m pytest -q -p no:cacheprovider -x tests/test_tp_gpu.py -m gpu
 fi
+if [ "$N" = "8" ]; then
+  run tp_check 300 $TR --master-port 29541 tools/tp_check.py
+fi
 if [ "$N" = "4" ]; then
   run quick 120 python -m pytest -q -p no:cacheprovider -x --timeout 40 tests/test_kernels_gpu.py -m gpu -k "fused_moe or argmax or rmsnorm"
 fi
