@@ -29,7 +29,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //   r += x (stored back in the activation dtype), y = round(r_f32 * rrms) * w
 // --------------------------------------------------------------------------- //
 template <typename T, int VPT_MAX>
-__global__ void __launch_bounds__(256) skip_rmsnorm_block_kernel(T* __restrict__ y, const T* __restrict__ x,
+__global__ void __launch_bounds__(512) skip_rmsnorm_block_kernel(T* __restrict__ y, const T* __restrict__ x,
                                                                  T* __restrict__ res, const T* __restrict__ w,
                                                                  int64_t n, int64_t x_stride, int64_t r_stride,
                                                                  int64_t y_stride, float eps) {
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) skip_rmsnorm_block_kernel(T* __restrict__
       for (int j = 0; j < 8; ++j) ss += vals[i][j] * vals[i][j];
     }
   }
-  __shared__ float red[8];
+  __shared__ float red[16];
   ss = warp_reduce_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
@@ -176,9 +176,12 @@ static int launch_skip_rmsnorm(void* y, const void* x, void* res, const void* w,
                        (res == nullptr || (uintptr_t)res % 16 == 0);
   if (aligned && n >= 1024 && n <= 8 * 256 * 8) {
     // one CTA per row
+    // decode rows are latency-bound (32 rows of 4096): one 16-byte chunk per thread puts every load of the row in
+    // flight at once (512 threads for hidden 4096); wider rows keep 256 threads and several chunks per thread
     int threads = 256;
     int64_t chunks = n / 8;
     if (chunks <= 128) threads = 128;
+    else if (chunks <= 512 && chunks > 256) threads = 512;
     int vpt = (int)cdiv64(chunks, threads);
     T* yy = (T*)y; const T* xx = (const T*)x; T* rr = (T*)res; const T* ww = (const T*)w;
     if (vpt <= 1)

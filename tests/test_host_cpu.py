@@ -206,3 +206,41 @@ def test_moe_expert_sharding_matches_the_reference_partition():
     m8 = make_moe_weights(cfg, router, gate, up, down, "fp8", 4, 1, torch.float16)     # 128 / 4 = 32 columns per rank
     assert m8.group_n == 32 and m8.group_k == 32 and m8.w1.dtype == torch.uint8
     assert m8.w1_scale.shape == (e, 2, h // 32) and m8.w2_scale.shape == (e, h // 32, 1)
+
+
+def test_awq_and_gptq_checkpoint_tensors_convert_to_the_reference_layout():
+    """AutoAWQ GEMM / AutoGPTQ tensors -> reference W4A16 layout (quantization/awq.py). The checkpoint side is packed
+    here with each format's published rule (AutoAWQ: eight output channels per word, order [0,2,4,6,1,3,5,7];
+    AutoGPTQ: eight input channels per word, zero points stored minus one), the converted tensors must dequantise
+    (oracle.ops.dequant_int4) to exactly (q - z) * s of the source integers."""
+    from lite_llama_b200.quantization.awq import AWQ_ORDER, awq_to_reference, gptq_to_reference
+    from oracle import ops
+
+    g = torch.Generator().manual_seed(0)
+    K_, N_, gs = 256, 64, 128
+    q = torch.randint(0, 16, (K_, N_), generator=g)                     # [K, N] integer weights
+    z = torch.randint(0, 16, (K_ // gs, N_), generator=g)
+    s = (torch.rand(K_ // gs, N_, generator=g) * 0.02 + 0.001).half()
+    want = ((q - z.repeat_interleave(gs, 0)).float() * s.float().repeat_interleave(gs, 0)).t()     # [N, K]
+
+    def pack_cols(t, order):                                            # eight columns per int32 word
+        w = torch.zeros(t.shape[0], t.shape[1] // 8, dtype=torch.int64)
+        for p, o in enumerate(order):
+            w |= t[:, o::8].to(torch.int64) << (4 * p)
+        return torch.where(w >= 2**31, w - 2**32, w).to(torch.int32)
+
+    qw, sc, zp = awq_to_reference(pack_cols(q, AWQ_ORDER), pack_cols(z, AWQ_ORDER), s)
+    assert qw.shape == (N_, K_ // 8) and sc.shape == zp.shape == (N_, K_ // gs)
+    assert torch.equal(ops.dequant_int4(qw, sc, zp, gs), want)
+
+    rows = torch.zeros(K_ // 8, N_, dtype=torch.int64)                  # GPTQ: eight input rows per word
+    for i in range(8):
+        rows |= q[i::8].to(torch.int64) << (4 * i)
+    rows = torch.where(rows >= 2**31, rows - 2**32, rows).to(torch.int32)
+    qw2, sc2, zp2 = gptq_to_reference(rows, pack_cols((z - 1) % 16, range(8)), s, g_idx=torch.arange(K_) // gs)
+    # zero points of 0 wrap to 15 in the 4-bit "minus one" storage; restrict the comparison to the others
+    ok = (z.t() > 0).repeat_interleave(gs, 1)
+    got = ops.dequant_int4(qw2, sc2, zp2, gs)
+    assert torch.equal(got[ok], want[ok]) and torch.equal(qw2, qw)
+    with pytest.raises(ValueError):
+        gptq_to_reference(rows, pack_cols((z - 1) % 16, range(8)), s, g_idx=torch.randperm(K_) // gs)
