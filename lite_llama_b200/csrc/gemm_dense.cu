@@ -184,15 +184,26 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
           uint32_t v[CH];
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] = 0u;
-          for (int s = 0; s < p.splits; ++s) {
-            const uint32_t* src = base + (size_t)s * (BT * kBlockW) + c * kBlockW + epi_tid;
+          // four splits' worth of loads in flight before the first addition (one L2 round trip per batch instead of
+          // one per split); the sums still run in split order, the padding zeros of a short batch change nothing
+          for (int s0 = 0; s0 < p.splits; s0 += 4) {
+            uint32_t w[4][CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const uint32_t w = __ldcg(src + j * kBlockW);
-              if (KIND == 0)
-                v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w));
-              else
-                v[j] = (uint32_t)((int)v[j] + (int)w);
+            for (int u = 0; u < 4; ++u) {
+              const bool on = s0 + u < p.splits;
+              const uint32_t* src = base + (size_t)(s0 + u) * (BT * kBlockW) + c * kBlockW + epi_tid;
+#pragma unroll
+              for (int j = 0; j < CH; ++j) w[u][j] = on ? __ldcg(src + j * kBlockW) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                if (KIND == 0)
+                  v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[u][j]));
+                else
+                  v[j] = (uint32_t)((int)v[j] + (int)w[u][j]);
+              }
             }
           }
           finish(c, v);

@@ -86,16 +86,39 @@ enum { DBG_FORCE_XSUM = 8, DBG_RAW_OPERAND = 16, DBG_PAIR_K4 = 32, DBG_NO_STREAM
        DBG_NO_XLOAD = 4096 /* activation tiles are never fetched */, DBG_HALF_RING = 8192 /* half the weight ring depth */,
        DBG_LEGACY_OPRING = 16384 /* round-1 operand-ring indexing (phase-aliasing hang repro; results may be wrong) */,
        DBG_FORCE = 32768 /* no experiment: just run the DBG instantiation (prices its code size) */ };
+// Wait flavour of the hand-off barriers (0: try_wait with the long suspend hint, 1: test_wait polling, 2: try_wait
+// with the default suspend window).  B2L_QWAIT_MODE covers every wait, B2L_QWAIT_LAT_MODE the latency-critical
+// ones (operand stage full / free, accumulator full): A/B builds, see tools/build_variants.py.
+#ifndef B2L_QWAIT_MODE
+#define B2L_QWAIT_MODE 0
+#endif
+#ifndef B2L_QWAIT_LAT_MODE
+#define B2L_QWAIT_LAT_MODE B2L_QWAIT_MODE
+#endif
+// Dequant warps: 0 = wait for the operand stage before converting a sub-block, 1 = convert first, wait before the store
+#ifndef B2L_DQ_ORDER
+#define B2L_DQ_ORDER 0
+#endif
+template <int MODE>
 __device__ __forceinline__ void qwait_at(uint64_t* bar, uint32_t parity, int debug, int line) {
   constexpr unsigned int fh = b2l_file_hash(__FILE__);
-  if (debug & DBG_WAIT_SPIN) mbar_wait_spin_at(bar, parity, fh, line);
-  else if (debug & DBG_WAIT_SHORT) mbar_wait_short_at(bar, parity, fh, line);
+  if ((debug & DBG_WAIT_SPIN) || MODE == 1) mbar_wait_spin_at(bar, parity, fh, line);
+  else if ((debug & DBG_WAIT_SHORT) || MODE == 2) mbar_wait_short_at(bar, parity, fh, line);
   else mbar_wait_at(bar, parity, fh, line);
 }
-#define qwait(bar, parity, debug) qwait_at((bar), (parity), (debug), __LINE__)
+#define qwait(bar, parity, debug) qwait_at<B2L_QWAIT_MODE>((bar), (parity), (debug), __LINE__)
+#define qwait_lat(bar, parity, debug) qwait_at<B2L_QWAIT_LAT_MODE>((bar), (parity), (debug), __LINE__)
 constexpr int kTlCta = 4096;    // timeline: [1024][3] per-CTA {globaltimer at entry, at exit, SM id}
 constexpr int kTlSub = 3072 + 32;   // timeline: [96][5] per-sub-block stamps of dequant warp 0
 constexpr int kTlMisc = 3072;   // timeline: start-up / shutdown stamps of CTA (0,0,0), see tools/timeline.py
+
+// B2L_TLITE (A/B builds only, tools/build_variants.py): a handful of clock stamps per CTA in the PRODUCT instantiation
+// (the DBG instantiation's own bookkeeping makes it ~50 % slower, so its timeline misplaces the critical path)
+#ifdef B2L_TLITE
+#define LT(i) do { if (p.timeline) p.timeline[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
+#else
+#define LT(i) do {} while (0)
+#endif
 
 // role rows of the debug timeline
 enum { TL_PROD = 0, TL_MMA_READY = 1, TL_MMA_ISSUED = 2, TL_DQ_START = 3, TL_DQ_DONE = 4, TL_EPI_START = 5, TL_EPI_DONE = 6 };
@@ -122,6 +145,8 @@ struct __align__(8) QControl {
   // tiles this CTA finished last (stream-K / split-K): reduced by ALL threads after the role loops
   int nfix;
   int fix_tile[4], fix_ntile[4], fix_sharers[4];
+  // shared tiles whose partial sums are written but whose tickets have not been taken yet (see flush_tickets)
+  int pend_tile[4], pend_ntile[4], pend_sharers[4];
 };
 static_assert(sizeof(QControl) <= 1024, "control block too large");
 
@@ -153,8 +178,10 @@ struct WorkRange {
   }
 };
 // first / last stream-K CTA that owns a raw block of tile t
+// (32-bit arithmetic: the host only plans stream-K when total * (ctas + 1) fits; a 64-bit division is ~120
+// instructions and every thread of the CTA used to do two of them before the first weight request could leave)
 __device__ __forceinline__ int sk_owner(int lin_rb, int ctas, int total) {
-  return (int)((((long long)lin_rb + 1) * ctas - 1) / total);
+  return (int)((((unsigned)lin_rb + 1u) * (unsigned)ctas - 1u) / (unsigned)total);
 }
 
 // Four TMEM accumulator buffers: the epilogue's drain latency (wake-up, tcgen05.ld, FMAs, arrive) is several
@@ -323,7 +350,7 @@ __device__ __forceinline__ void issue_block(QControl* ctl, uint32_t tmem_base, u
     const int segA = seg0 + (2 * sp) / SPS, segB = seg0 + (2 * sp + 1) / SPS;
     if ((2 * sp) % SPS == 0) qwait(&ctl->acc_empty[segA & (NB - 1)], ((segA / NB) & 1) ^ 1, debug);
     if (SPS == 1) qwait(&ctl->acc_empty[segB & (NB - 1)], ((segB / NB) & 1) ^ 1, debug);
-    qwait(&ctl->op_full[ostage], oparity, debug);
+    qwait_lat(&ctl->op_full[ostage], oparity, debug);
     tc_fence_after();
     if (elect_one()) {
       const uint32_t a_addr = a_base + ostage * 64;
@@ -363,6 +390,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   // debug flag or a timeline buffer is set): the product kernel carries none of their code
   const int debug = DBG ? p.debug : 0;
   long long* const timeline = DBG ? p.timeline : nullptr;
+  // first thing: the TMA unit starts fetching the weight descriptor while the CTA works out its range (the first
+  // weight request otherwise waits for the descriptor AND for the data: two dependent trips to memory)
+  if (threadIdx.x == kWarpWProd * 32) tma_prefetch_desc(&tmap_w);
+#ifdef B2L_TLITE
+  if (threadIdx.x == 0) LT(23);
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   QControl* ctl = reinterpret_cast<QControl*>(smem);
@@ -400,12 +433,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   WorkRange wr;
   int k_begin, steps_total;                       // legacy grid only: the single piece's first K and its MMA steps
   if (p.sk_ctas > 0) {
-    const int total = p.n_tiles * p.nrb_tile;
+    const unsigned total = (unsigned)(p.n_tiles * p.nrb_tile);
     wr.nrb_tile = p.nrb_tile;
-    wr.g0 = (int)(((long long)blockIdx.x * total) / p.sk_ctas);
-    wr.g1 = (int)(((long long)(blockIdx.x + 1) * total) / p.sk_ctas);
-    wr.t0 = wr.g0 / p.nrb_tile;
-    wr.npieces = (wr.g1 - 1) / p.nrb_tile - wr.t0 + 1;
+    wr.g0 = (int)((blockIdx.x * total) / (unsigned)p.sk_ctas);
+    wr.g1 = (int)(((blockIdx.x + 1u) * total) / (unsigned)p.sk_ctas);
+    wr.t0 = (int)((unsigned)wr.g0 / (unsigned)p.nrb_tile);
+    wr.npieces = (int)((unsigned)(wr.g1 - 1) / (unsigned)p.nrb_tile) - wr.t0 + 1;
     wr.total_rb = wr.g1 - wr.g0;
     wr.legacy_tile = wr.legacy_lo = wr.legacy_hi = 0;
     k_begin = 0;
@@ -429,6 +462,18 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int mma_warps = p.aligned ? 2 : 1;
 
   if (tl && threadIdx.x == 0) tl[kTlMisc + 0] = clock64();
+#ifdef B2L_TLITE
+  if (threadIdx.x == 0) {
+    LT(0);
+    if (p.timeline) {
+      unsigned long long gt; unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.timeline[(size_t)blockIdx.x * 32 + 16] = (long long)gt;
+      p.timeline[(size_t)blockIdx.x * 32 + 18] = (long long)smid;
+    }
+  }
+#endif
   // every CTA: wall-clock (globaltimer, ns) at entry and exit + its SM id -> who is the straggler, and what is the
   // real SM clock (CTA 0 also stamps clock64 at both ends)
   if (timeline && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 1024) {
@@ -545,58 +590,66 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 7] = clock64();
   }
 
+  if (LAYOUT == 1 && warp == kWarpXProd && lane == 0) {
+    // packed tables: a piece's groups x 128 rows are contiguous in global memory -> one bulk copy per table and
+    // piece.  Requested by the activation producer's lane (idle until griddepcontrol.wait; the tables are weights)
+    // while the weight producer initialises its ring and sends its first requests: issued one after the other by
+    // a single lane, the table copies alone kept the first weight request back by ~0.7 us (per-CTA stamps, profiles/).
+    mbar_init(&ctl->tab_full, 1);
+    mbar_fence_init();
+    fence_proxy_async_smem();
+    const int G = p.K / seg_len;
+    const int gpr = RW >> p.seg_shift;               // scale groups per raw block (stream-K: the raw block holds whole groups)
+    int total_cols = 0;
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      if (p.sk_ctas > 0) total_cols += (pc.rb_hi - pc.rb_lo) * gpr;
+      else total_cols += (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len + 1;
+    }
+    mbar_arrive_expect_tx(&ctl->tab_full, (uint32_t)total_cols * kBlockW * 4 * 2);
+    int tcol = 0;
+    for (int pi = 0; pi < wr.npieces; ++pi) {
+      const Piece pc = wr.piece(pi);
+      int g_first, g_count;
+      if (p.sk_ctas > 0) {
+        g_first = pc.rb_lo * gpr;
+        g_count = (pc.rb_hi - pc.rb_lo) * gpr;
+      } else {
+        g_first = k_begin / seg_len;
+        g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
+      }
+      const size_t src = ((size_t)pc.n_tile * G + g_first) * kBlockW;
+      bulk_g2s(zero_tab + tcol * kBlockW, p.zeros + src, (uint32_t)g_count * kBlockW * 4, &ctl->tab_full);
+      bulk_g2s(scale_tab + tcol * kBlockW, p.scales + src, (uint32_t)g_count * kBlockW * 4, &ctl->tab_full);
+      tcol += g_count;
+    }
+    LT(19);
+  }
   if (warp == kWarpWProd) {
     if (lane == 0) {
       // Order matters for the launch latency of the short GEMMs (a CTA of the qkv / o projections converts 3-5 raw
       // blocks in all): only what the first requests need is initialised before they are issued -- the weight ring's
-      // barriers, the tables, the first ring-full of weights -- and the other ~30 barriers afterwards (the device
-      // timeline showed the first weight request leaving 2400 cycles after kernel entry, most of it this lane's set-up).
-      tma_prefetch_desc(&tmap_w);
+      // barriers, then the first ring-full of weights -- and the other ~30 barriers afterwards (the device timeline
+      // showed the first weight request leaving 2400 cycles after kernel entry, most of it this lane's set-up).
+      LT(24);
       for (int s = 0; s < p.w_stages; ++s) {
         mbar_init(&ctl->w_full[s], 1);
         mbar_init(&ctl->w_empty[s], 4);        // the 4 dequant warps that convert the block
       }
-      if (LAYOUT == 1) mbar_init(&ctl->tab_full, 1);
       ctl->nfix = 0;
+      LT(25);
       mbar_fence_init();
       fence_proxy_async_smem();
-      if (LAYOUT == 1) {
-        // packed tables: a piece's groups x 128 rows are contiguous in global memory -> one bulk copy per table
-        // and piece, requested before the weight stream so that they are not queued behind it
-        const int G = p.K / seg_len;
-        int total_cols = 0;
-        for (int pi = 0; pi < wr.npieces; ++pi) {
-          const Piece pc = wr.piece(pi);
-          if (p.sk_ctas > 0) total_cols += (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
-          else total_cols += (k_begin + steps_total * 16 - 1) / seg_len - k_begin / seg_len + 1;
-        }
-        mbar_arrive_expect_tx(&ctl->tab_full, (uint32_t)total_cols * kBlockW * 4 * 2);
-        int tcol = 0;
-        for (int pi = 0; pi < wr.npieces; ++pi) {
-          const Piece pc = wr.piece(pi);
-          int g_first, g_count;
-          if (p.sk_ctas > 0) {
-            g_first = pc.rb_lo * kRawK / seg_len;
-            g_count = (pc.rb_hi - pc.rb_lo) * kRawK / seg_len;
-          } else {
-            g_first = k_begin / seg_len;
-            g_count = (k_begin + steps_total * 16 - 1) / seg_len - g_first + 1;
-          }
-          const size_t src = ((size_t)pc.n_tile * G + g_first) * kBlockW;
-          bulk_g2s(zero_tab + tcol * kBlockW, p.zeros + src, (uint32_t)g_count * kBlockW * 4, &ctl->tab_full);
-          bulk_g2s(scale_tab + tcol * kBlockW, p.scales + src, (uint32_t)g_count * kBlockW * 4, &ctl->tab_full);
-          tcol += g_count;
-        }
-      }
+      LT(26);
       if (tl) tl[kTlMisc + 8] = clock64();
     }
     __syncwarp();
     // Weights are static: under programmatic dependent launch this stream starts while the previous kernel is
-    // still running (no griddepcontrol.wait on this path) -- and before the rest of the CTA has finished setting up,
-    // but after the table requests are on their way (see above).
+    // still running (no griddepcontrol.wait on this path) -- and before the rest of the CTA has finished setting up.
     if (LAYOUT == 0) asm volatile("bar.sync 5, %0;" ::"n"((kFillWarps + 1) * 32) : "memory");
     const int pre = nrb < p.w_stages ? nrb : p.w_stages;
     for (int i = 0; i < pre; ++i) w_issue(false);
+    if (lane == 0) LT(1);
     if (lane == 0) {
       // the rest of the set-up, behind the first requests; published to the other warps by the set-up barrier below
       tma_prefetch_desc(&tmap_x);
@@ -633,6 +686,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   if (tl && threadIdx.x == 0) tl[kTlMisc + 1] = clock64();
+  if (threadIdx.x == 0) LT(2);
 
   if (warp == kWarpWProd) {
     // ===================== weight producer (whole warp loops, one elected lane issues) =====================
@@ -640,6 +694,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   } else if (warp == kWarpXProd) {
     // ===================== activation producer =====================
     pdl_wait_prior();                        // the activations are the previous kernel's output
+    if (lane == 0) LT(3);
     PipeState xs(p.x_stages);
     for (int pi = 0; pi < wr.npieces; ++pi) {
       const Piece pc = wr.piece(pi);
@@ -680,6 +735,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         qwait(&ctl->x_full[rstage], rphase, debug);                         // activation sub-tiles (TMA)
         tc_fence_after();
         TL_STAMP(TL_MMA_READY, rb);
+        if (rb == 0 && lane == 0) LT(4);
         int steps_here = steps_total - rb * (RW * 4);
         if (steps_here > RW * 4) steps_here = RW * 4;
         if (mma_warps == 2) {
@@ -703,7 +759,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               int ostage; uint32_t oparity;                      // operand stage = two sub-blocks
               op_slot<kOpStages, RW / 2>(rb, st >> 3, ostage, oparity, debug);
               if ((st & 7) == 0) {
-                qwait(&ctl->op_full[ostage], oparity, debug);   // dequantised stage
+                qwait_lat(&ctl->op_full[ostage], oparity, debug);   // dequantised stage
                 tc_fence_after();
               }
               if (!seg_open) {
@@ -731,6 +787,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
         __syncwarp();
         TL_STAMP(TL_MMA_ISSUED, rb);
+        if (rb == 0 && lane == 0) LT(5);
+        if (rb + mma_warps >= nrb && lane == 0) LT(6 + mma_idx);
         rstage += mma_warps;
         if (rstage >= p.x_stages) { rstage -= p.x_stages; rphase ^= 1; }
       }
@@ -759,6 +817,25 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
     int seg = 0;                                           // segments and table columns run linearly over the pieces
     int tcol = 0;
+    int npend = 0;                                         // shared tiles written, tickets outstanding (uniform)
+    auto flush_tickets = [&]() {
+      __threadfence();                                     // every partial tile written so far is visible device-wide ...
+      asm volatile("bar.sync 2, 128;" ::: "memory");       // ... for all 128 writers, before any ticket is taken
+      if (epi_tid < npend) {
+        // Last finisher of a tile: its partial sums are added up by ALL 512 threads once the role loops are over (end
+        // of the kernel): 128 epilogue threads walking the slots made the tail of the short GEMMs ~5 us long.
+        const int tile = ctl->pend_tile[epi_tid], sh = ctl->pend_sharers[epi_tid];
+        const int old = atomicAdd(&p.counters[tile], 1);
+        if (old == sh - 1) {
+          p.counters[tile] = 0;                            // self-reset: the next launch (or graph replay) starts clean
+          const int f = atomicAdd(&ctl->nfix, 1);
+          if (f >= 4) __trap();                            // cannot happen: at most two shared pieces per CTA
+          ctl->fix_tile[f] = tile; ctl->fix_ntile[f] = ctl->pend_ntile[epi_tid]; ctl->fix_sharers[f] = sh;
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      npend = 0;
+    };
     for (int pi = 0; pi < wr.npieces; ++pi) {
       const Piece pc = wr.piece(pi);
       const int n = pc.n_tile * kBlockW + epi_tid;
@@ -801,9 +878,10 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const float sc = lds_f32(scale_tab + tcol * TP + epi_tid);        // rows past N hold zeros
         float zp = 0.f;
         if (QK == Q_INT4 && need_xsum) zp = lds_f32(zero_tab + tcol * TP + epi_tid);
-        qwait(&ctl->acc_full[buf], (seg / NB) & 1, debug);
+        qwait_lat(&ctl->acc_full[buf], (seg / NB) & 1, debug);
         tc_fence_after();
         if (warp == kWarpEpi0) TL_STAMP(TL_EPI_START, seg);
+        if (warp == kWarpEpi0 && lane == 0 && seg == 0) LT(12);
         if ((debug & DBG_SKIP_DRAIN) && k_next < k_lim) {
           tc_fence_before();
           __syncwarp();
@@ -850,6 +928,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
       // ---- the piece is complete: write the tile, or hand the partial sum to the tile's last finisher ----
       if (tl && warp == kWarpEpi0 && lane == 0 && pi == wr.npieces - 1) tl[kTlMisc + 5] = clock64();
+      if (warp == kWarpEpi0 && lane == 0 && pi == wr.npieces - 1) LT(13);
       pdl_wait_prior();              // output / workspace buffers may still be in use by the previous kernel
       auto store_final = [&]() {
         float bv = 0.f;
@@ -874,10 +953,19 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           return;
         }
         if (!n_ok) return;
+        // one running pointer and one row-count test for the whole tile: this runs on the CTA's critical path (the
+        // per-row index arithmetic and bounds tests made the tile store ~600 instructions per thread, 1.3 us)
+        T* yp = y + (int64_t)(m_tile * BT) * p.ldy + n;
+        const int rows = p.M - m_tile * BT;
+        if (rows >= BT) {
 #pragma unroll
-        for (int j = 0; j < BT; ++j) {
-          const int m = m_tile * BT + j;
-          if (m < p.M) y[(int64_t)m * p.ldy + n] = __float2half_rn(acc[j] + bv);
+          for (int j = 0; j < BT; ++j) { *yp = __float2half_rn(acc[j] + bv); yp += p.ldy; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < BT; ++j) {
+            if (j < rows) *yp = __float2half_rn(acc[j] + bv);
+            yp += p.ldy;
+          }
         }
       };
       // who shares this tile: legacy grid = the p.splits CTAs along grid.z; stream-K = the CTAs whose ranges
@@ -901,33 +989,19 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         uint32_t* mine = base + (size_t)slot * (BT * kBlockW);
 #pragma unroll
         for (int j = 0; j < BT; ++j) mine[j * kBlockW + epi_tid] = __float_as_uint(acc[j]);
-        if (splitk_ticket(p.counters, tile_id, sharers, epi_tid, &ctl->is_last)) {
-          // Last finisher of the tile.  The partial sums are added up by ALL 512 threads once the role loops are over
-          // (end of the kernel): 128 epilogue threads walking the slots one after the other made the tail of the
-          // short GEMMs ~5 us long (per-CTA wall clock, profiles/r1b_cta_wallclock.txt).  Only when the small list is
-          // full (more than 4 finished tiles per CTA: tiny K) is the tile reduced right here.
-          const int f = ctl->nfix;             // written by epi_tid 0 only ...
-          asm volatile("bar.sync 2, 128;" ::: "memory");   // ... after every epilogue thread has read it
-          if (f < 4) {
-            if (epi_tid == 0) {
-              ctl->fix_tile[f] = tile_id; ctl->fix_ntile[f] = pc.n_tile; ctl->fix_sharers[f] = sharers;
-              ctl->nfix = f + 1;               // next read: behind the barriers of the next tile's ticket
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < BT; ++j) acc[j] = 0.f;
-            for (int s = 0; s < sharers; ++s) {
-              const uint32_t* src = base + (size_t)s * (BT * kBlockW) + epi_tid;
-#pragma unroll
-              for (int j = 0; j < BT; ++j) acc[j] += __uint_as_float(__ldcg(src + j * kBlockW));
-            }
-            store_final();
-          }
-        }
+        // The ticket is NOT taken here: fence + atomic are two L2 round trips (~1.4 us, per-CTA stamps under profiles/)
+        // during which no accumulator was drained -- a CTA whose range crosses a tile boundary stalled its MMA warps
+        // in the middle of the kernel and became the straggler of the grid.  The tile is queued and all tickets are
+        // taken together after the last piece (one fence, overlapping atomics).  At most two pieces of a range are
+        // shared (its first and last tile), the queue holds four.
+        if (epi_tid == 0) { ctl->pend_tile[npend] = tile_id; ctl->pend_ntile[npend] = pc.n_tile; ctl->pend_sharers[npend] = sharers; }
+        if (++npend == 4) flush_tickets();
       }
 #pragma unroll
       for (int j = 0; j < BT; ++j) acc[j] = 0.f;
     }
+    if (npend > 0) flush_tickets();
+    if (warp == kWarpEpi0 && lane == 0) LT(14);
   } else {
     // ===================== dequant warps 0..7: thread = one weight row of every second raw block =====================
     // A warp may only touch the TMEM lane quadrant (warp id % 4).  Warps 0..3 convert the even raw blocks,
@@ -985,6 +1059,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->w_empty[rstage]);
       if (quad == 0) TL_STAMP(TL_DQ_START, rb);
+      if (warp == 0 && lane == 0 && rb == 0) LT(8);
       // one operand sub-stage per 64-element sub-block; the "sub-block ready" arrive of sub-block s is issued
       // after the conversion of s+1, so tcgen05.wait::st never waits for a store that was just issued
       int pending = -1;
@@ -999,8 +1074,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (gsub < nsub_total) {                               // sub-blocks past the k-range have no MMA step
           int ostage; uint32_t oparity;                        // operand stage = sub-blocks (2i, 2i+1); rb * RW is even
           op_slot<kOpStages, RW / 2>(rb, sub >> 1, ostage, oparity, debug);
-          if ((sub & 1) == 0) {
-            qwait(&ctl->op_empty[ostage], oparity ^ 1, debug);
+          if (B2L_DQ_ORDER == 0 && (sub & 1) == 0) {
+            qwait_lat(&ctl->op_empty[ostage], oparity ^ 1, debug);
             tc_fence_after();
           }
           if (tls) tls[1] = clock64();
@@ -1059,6 +1134,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
             pending = -1;
           }
+          // the operand stage is only needed for the store: waiting for it here, after the conversion and after the
+          // previous stage has been announced, keeps a late stage from delaying either
+          if (B2L_DQ_ORDER == 1 && (sub & 1) == 0) {
+            qwait_lat(&ctl->op_empty[ostage], oparity ^ 1, debug);
+            tc_fence_after();
+          }
           if (tls) tls[3] = clock64();
           if (!(debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 64 + (sub & 1) * 32, vals);
           else asm volatile("" ::"r"(vals[0] ^ vals[7] ^ vals[13] ^ vals[31]));
@@ -1073,6 +1154,8 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
       }
       if (quad == 0) TL_STAMP(TL_DQ_DONE, rb);
+      if (warp == 0 && lane == 0 && rb == 0) LT(9);
+      if (quad == 0 && lane == 0 && rb + 2 >= nrb) LT(10 + half);
       rstage += 2;
       if (rstage >= p.w_stages) { rstage -= p.w_stages; rphase ^= 1; }
     }
@@ -1080,9 +1163,17 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+#ifdef B2L_TLITE
+  if (threadIdx.x == 0 && p.timeline) {     // (the clock read is tied to a value loaded after the barrier: ptxas hoists it otherwise)
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(ctl->nfix) : "memory");
+    p.timeline[(size_t)blockIdx.x * 32 + 15] = t;
+  }
+#endif
   // ---- split tiles this CTA finished last: out = sum of the partial tiles in slot order (deterministic) + bias ----
   {
     const int nfix = ctl->nfix;
+    if (nfix > 0) __threadfence();
     const int slots_per_tile = p.sk_ctas > 0 ? p.sk_slots : p.splits;
     constexpr int JT = kQuantThreads / kBlockW;            // token rows covered per pass (4)
     constexpr int NJ = BT / JT;
@@ -1093,11 +1184,31 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       float sum[NJ];
 #pragma unroll
       for (int i = 0; i < NJ; ++i) sum[i] = 0.f;
-      for (int s0 = 0; s0 < sharers; ++s0) {
+      // every partial value of up to SB slots is requested before the first one is used: the loads are L2 round trips
+      // (~1 us each when issued one slot at a time: 5 us for the o projection's 5 sharers, per-CTA stamps under
+      // profiles/); the additions still run in slot order (+0.0f for the slots past the last sharer changes nothing)
+      constexpr int SB = NJ <= 8 ? 8 : 4;
+      for (int s0 = 0; s0 < sharers; s0 += SB) {
+        float v[SB][NJ];
 #pragma unroll
-        for (int i = 0; i < NJ; ++i)
-          sum[i] += __uint_as_float(__ldcg(base + (size_t)s0 * (BT * kBlockW) + (j_first + i * JT) * kBlockW));
+        for (int u = 0; u < SB; ++u) {
+          const bool on = s0 + u < sharers;
+#pragma unroll
+          for (int i = 0; i < NJ; ++i)
+            v[u][i] = on ? __uint_as_float(__ldcg(base + (size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW)) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < SB; ++u)
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) sum[i] += v[u][i];
       }
+#ifdef B2L_TLITE
+      if (threadIdx.x == 0 && p.timeline && f == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(sum[0]) : "memory");
+        p.timeline[(size_t)blockIdx.x * 32 + 27] = t;
+      }
+#endif
       const int n = ctl->fix_ntile[f] * kBlockW + n_local;
       const bool n_ok = n < p.N;
       float bv = 0.f;
@@ -1126,6 +1237,16 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     timeline[kTlCta + 3 * blockIdx.x + 1] = (long long)gt;
   }
+#ifdef B2L_TLITE
+  if (threadIdx.x == 0 && p.timeline) {
+    LT(20);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.timeline[(size_t)blockIdx.x * 32 + 17] = (long long)gt;
+    p.timeline[(size_t)blockIdx.x * 32 + 21] = ctl->nfix;
+    p.timeline[(size_t)blockIdx.x * 32 + 22] = nrb;
+  }
+#endif
   if (warp == kWarpMma0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -1190,7 +1311,8 @@ static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int 
   {
     const int raw_k = qk == Q_INT4 ? 256 : 128;
     const bool aligned = raw_k % seg_len == 0 && raw_k / seg_len <= 2;     // same rule as QuantParams::aligned
-    if (streamk_enabled() && !(g_debug & DBG_NO_STREAMK) && aligned && K % raw_k == 0 && pl.m_tiles == 1) {
+    if (streamk_enabled() && !(g_debug & DBG_NO_STREAMK) && aligned && K % raw_k == 0 && pl.m_tiles == 1 &&
+        (int64_t)pl.n_tiles * (K / raw_k) < (1 << 22)) {        // the kernel's range arithmetic is 32-bit: total * (ctas + 1)
       const int nrb_tile = (int)(K / raw_k);
       const int64_t total = (int64_t)pl.n_tiles * nrb_tile;
       int ctas = (int)(total / 2 < sms ? total / 2 : sms);                 // at least two raw blocks per CTA
@@ -1257,7 +1379,11 @@ static int launch_q_inst(const CUtensorMap& tw, const CUtensorMap& tx, const Qua
 template <int QK, int BT>
 static int launch_q_bt(const CUtensorMap& tw, const CUtensorMap& tx, const QuantParams& p, const SplitPlan& pl,
                        cudaStream_t st, int layout) {
+#ifdef B2L_TLITE
+  const bool dbg = p.debug != 0;
+#else
   const bool dbg = p.debug != 0 || p.timeline != nullptr;
+#endif
   if constexpr (QK == Q_INT4) {
     if (layout == 1) {
       if (p.swiglu) {
