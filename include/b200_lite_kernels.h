@@ -22,6 +22,9 @@
  *   - workspaces: `b2l_*_workspace_bytes` are pure functions of shapes (+ SM count), so the caller
  *     can size a torch.empty scratch buffer outside graph capture.  Split-K GEMMs additionally take a
  *     small int32 `counters` array that must be ZERO on entry; kernels leave it zero on exit.
+ *     The QUANTISED GEMMs' workspace (b2l_w4a16_matmul*, b2l_w8a16_matmul) carries stream-K partial sums as
+ *     tagged words (flag-in-data): it must be ZERO on entry as well and is left zero on exit, so keep ONE persistent,
+ *     once-zeroed buffer per device (and one stream of launches), exactly like `counters`.
  */
 #ifndef B200_LITE_KERNELS_H
 #define B200_LITE_KERNELS_H

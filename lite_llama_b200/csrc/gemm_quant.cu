@@ -808,6 +808,23 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // segment's activation row sums (computed here from global memory; rare, correctness path only).  The
     // decision was taken by the table-fill threads and ORed across the CTA by the set-up barrier.
     const bool need_xsum = QK == Q_INT4 && cta_need_xsum;
+    if (p.sk_ctas > 0 && warp == kWarpEpi0) {
+      // The reducer of a shared tile (see the end of the kernel) reads the other sharers' workspace slots exactly once,
+      // at the very end, with every other warp waiting for it: the first access of this SM to those pages took ~1.3 us
+      // whatever the amount of data (per-CTA stamps, profiles/) -- an address translation miss.  One throw-away
+      // gpu-scope load per slot now, while this warp has nothing to do, takes the miss off the critical path (no L1
+      // allocation: the slots are polled with ordinary loads later).  The value is not used, so it does not matter
+      // that the previous kernel may still be clearing the words.
+      const Piece lp = wr.piece(wr.npieces - 1);
+      const int total = p.n_tiles * p.nrb_tile;
+      const int c_lo = sk_owner(lp.n_tile * p.nrb_tile, p.sk_ctas, total);
+      const int c_hi = sk_owner((lp.n_tile + 1) * p.nrb_tile - 1, p.sk_ctas, total);
+      if (c_lo == (int)blockIdx.x && lane > 0 && lane <= c_hi - c_lo) {
+        const uint32_t* a = p.ws + ((size_t)lp.n_tile * p.sk_slots + lane) * (BT * kBlockW);
+        uint32_t d;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(a) : "memory");
+      }
+    }
     if (LAYOUT == 1) mbar_wait(&ctl->tab_full, 0);
     if (need_xsum) pdl_wait_prior();   // the fallback reads the activations (the previous kernel's output) from global
     if (tl && warp == kWarpEpi0 && lane == 0) tl[kTlMisc + 3] = clock64();
@@ -983,6 +1000,33 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       if (sharers == 1) {
         store_final();
+      } else if (p.sk_ctas > 0) {
+        // ---- stream-K: flag-in-data hand-over to the tile's first sharer ----
+        // A partial value travels as ONE 32-bit word whose lowest mantissa bit is forced to 1 ("present"; a cleared
+        // word is 0): a reader that sees the bit has the value, so the writer needs neither a fence nor a ticket --
+        // it stores and moves on.  (The bit costs <= 2^-24 relative on a partial sum, 2^13 times below the fp16
+        // output's resolution, and is the same in every run: results stay deterministic.)  The reducer is the CTA of
+        // slot 0: the tile is the LAST piece of its range (its range starts at or before the tile and ends inside
+        // it), so it gets there when everybody else is about done, keeps its own partial sum on chip and reads the
+        // other slots once all 512 threads are free (end of the kernel), clearing the words behind it: the workspace
+        // is all-zero between launches (contract of the C ABI, like the ticket counters).  Ticket protocol before:
+        // fence + atomic (two L2 round trips) on every sharer, then up to two serial tile reductions on whoever came
+        // last -- 3 to 5 us on the grid's critical path (per-CTA stamps, profiles/r2n_tlite*.txt).  All
+        // sk_ctas <= #SM CTAs are co-resident, so waiting for a sharer cannot dead-lock.
+        uint32_t* base32 = p.ws + (size_t)pc.n_tile * slots_per_tile * (BT * kBlockW);
+        if (slot != 0) {
+          uint32_t* mine = base32 + (size_t)slot * (BT * kBlockW) + epi_tid;
+#pragma unroll
+          for (int j = 0; j < BT; ++j) mine[j * kBlockW] = __float_as_uint(acc[j]) | 1u;
+        } else {
+          float* own = reinterpret_cast<float*>(w_ring);     // every raw block has been consumed: the ring is idle
+#pragma unroll
+          for (int j = 0; j < BT; ++j) own[j * kBlockW + epi_tid] = acc[j];
+          if (epi_tid == 0) {
+            ctl->fix_tile[0] = pc.n_tile; ctl->fix_ntile[0] = pc.n_tile; ctl->fix_sharers[0] = sharers;
+            ctl->nfix = 1;
+          }
+        }
       } else {
         const int tile_id = m_tile * p.n_tiles + pc.n_tile;
         uint32_t* base = p.ws + (size_t)tile_id * slots_per_tile * (BT * kBlockW);
@@ -1173,34 +1217,116 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   // ---- split tiles this CTA finished last: out = sum of the partial tiles in slot order (deterministic) + bias ----
   {
     const int nfix = ctl->nfix;
-    if (nfix > 0) __threadfence();
     const int slots_per_tile = p.sk_ctas > 0 ? p.sk_slots : p.splits;
     constexpr int JT = kQuantThreads / kBlockW;            // token rows covered per pass (4)
     constexpr int NJ = BT / JT;
     const int n_local = threadIdx.x % kBlockW, j_first = threadIdx.x / kBlockW;
+    if (p.sk_ctas == 0 && nfix > 0) __threadfence();
     for (int f = 0; f < nfix; ++f) {
       const int sharers = ctl->fix_sharers[f];
-      const uint32_t* base = p.ws + (size_t)ctl->fix_tile[f] * slots_per_tile * (BT * kBlockW) + n_local;
       float sum[NJ];
+      if (p.sk_ctas > 0) {
+        // ---- stream-K: this CTA is slot 0 of the tile; its own partial sum is in shared memory, the other slots'
+        // arrive as tagged words (see the epilogue).  Up to SB slots are requested together: the reduction is bound by
+        // the bytes one SM can pull out of L2 (~1.2 us for 128 KiB when the words were 8 bytes wide), not by latency.
+        // A word whose tag bit is not there yet is simply read again.  Sum in slot order, then clear what was read.
+        uint32_t* base = p.ws + (size_t)ctl->fix_tile[f] * slots_per_tile * (BT * kBlockW) + n_local;
+        const float* own = reinterpret_cast<const float*>(w_ring);
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) sum[i] = 0.f;
-      // every partial value of up to SB slots is requested before the first one is used: the loads are L2 round trips
-      // (~1 us each when issued one slot at a time: 5 us for the o projection's 5 sharers, per-CTA stamps under
-      // profiles/); the additions still run in slot order (+0.0f for the slots past the last sharer changes nothing)
-      constexpr int SB = NJ <= 8 ? 8 : 4;
-      for (int s0 = 0; s0 < sharers; s0 += SB) {
-        float v[SB][NJ];
+        for (int i = 0; i < NJ; ++i) sum[i] = own[(j_first + i * JT) * kBlockW + n_local];
+#ifdef B2L_TLITE
+        if (threadIdx.x == 0 && p.timeline) {
+          long long t;
+          asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(sum[0]) : "memory");
+          p.timeline[(size_t)blockIdx.x * 32 + 28] = t;
+          p.timeline[(size_t)blockIdx.x * 32 + 29] = 0;
+        }
+#endif
+        constexpr int SB = NJ <= 8 ? 6 : 3;
+        for (int s0 = 1; s0 < sharers; s0 += SB) {
+          uint32_t v[SB][NJ];
+          unsigned long long t0 = 0ull;
+          for (bool first = true;; first = false) {
+            // All requests first, the tag bits afterwards.  The first attempt uses ordinary loads (this SM has not
+            // touched these lines during the launch, L1 is clean); a retry must not be served by L1 and uses gpu-scope
+            // loads -- it was never needed in the measured runs: the reducer's tile is its last piece and the other
+            // sharers are done by then.
 #pragma unroll
-        for (int u = 0; u < SB; ++u) {
-          const bool on = s0 + u < sharers;
+            for (int u = 0; u < SB; ++u) {
+              const bool on = s0 + u < sharers;
+#pragma unroll
+              for (int i = 0; i < NJ; ++i) {
+                uint32_t w = 1u;                                   // a slot past the last sharer counts as "there"
+                const uint32_t* src = base + (size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW;
+                if (on) {
+                  if (first) asm volatile("ld.global.u32 %0, [%1];" : "=r"(w) : "l"(src) : "memory");
+                  else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(src) : "memory");
+                }
+                v[u][i] = w;
+              }
+            }
+            uint32_t all = 1u;
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+#pragma unroll
+              for (int i = 0; i < NJ; ++i) all &= v[u][i];
+#ifdef B2L_TLITE
+            if (threadIdx.x == 0 && p.timeline && s0 == 1) {
+              long long t;
+              asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(all) : "memory");
+              p.timeline[(size_t)blockIdx.x * 32 + 30] = t;
+            }
+#endif
+            if (all & 1u) break;
+#ifdef B2L_TLITE
+            if (threadIdx.x == 0 && p.timeline) p.timeline[(size_t)blockIdx.x * 32 + 29] += 1;
+#endif
+            // a sharer is still working (or, if this never ends, something is broken: trap with a record)
+            const unsigned long long now = b2l_globaltimer();
+            if (t0 == 0ull) t0 = now;
+            const unsigned long long lim = b2l_hang_ctl.limit_ns;
+            if (lim != 0ull && now - t0 > lim)
+              b2l_hang_trap((uint32_t)ctl->fix_tile[f], (uint32_t)s0, b2l_file_hash(__FILE__), __LINE__, now - t0);
+          }
+#pragma unroll
+          for (int u = 0; u < SB; ++u) {
+            if (s0 + u < sharers) {
+#pragma unroll
+              for (int i = 0; i < NJ; ++i) {
+                sum[i] += __uint_as_float(v[u][i]);
+                base[(size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW] = 0u;   // leave the workspace clean
+              }
+            }
+          }
+        }
+      } else {
+        const uint32_t* base = p.ws + (size_t)ctl->fix_tile[f] * slots_per_tile * (BT * kBlockW) + n_local;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) sum[i] = 0.f;
+        // every partial value of up to SB slots is requested before the first one is used: the loads are L2 round trips
+        // (~1 us each when issued one slot at a time: 5 us for the o projection's 5 sharers, per-CTA stamps under
+        // profiles/); the additions still run in slot order (+0.0f for the slots past the last sharer changes nothing)
+        constexpr int SB = NJ <= 8 ? 8 : 4;
+        for (int s0 = 0; s0 < sharers; s0 += SB) {
+          float v[SB][NJ];
+#pragma unroll
+          for (int u = 0; u < SB; ++u) {
+            const bool on = s0 + u < sharers;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i)
+              v[u][i] = on ? __uint_as_float(__ldcg(base + (size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW)) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < SB; ++u)
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) sum[i] += v[u][i];
+        }
+        // the workspace is shared with the stream-K launches, whose protocol needs it all-zero between launches
+        for (int s0 = 0; s0 < sharers; ++s0) {
 #pragma unroll
           for (int i = 0; i < NJ; ++i)
-            v[u][i] = on ? __uint_as_float(__ldcg(base + (size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW)) : 0.f;
+            const_cast<uint32_t*>(base)[(size_t)s0 * (BT * kBlockW) + (j_first + i * JT) * kBlockW] = 0u;
         }
-#pragma unroll
-        for (int u = 0; u < SB; ++u)
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) sum[i] += v[u][i];
       }
 #ifdef B2L_TLITE
       if (threadIdx.x == 0 && p.timeline && f == 0) {

@@ -66,6 +66,28 @@ def counters(device: torch.device) -> torch.Tensor:
     return buf
 
 
+# Stream-K partial sums of the quantised GEMMs travel through a workspace with flag-in-data words (csrc/gemm_quant.cu):
+# the buffer must be all-zero when a launch starts and every launch leaves it all-zero, so it is persistent and zeroed
+# once -- same contract (and same one-stream assumption) as the ticket counters above. A buffer that has to grow is
+# replaced, never freed: a captured CUDA graph may still hold its address.
+_ZEROED: dict[int, torch.Tensor] = {}
+_ZEROED_RETIRED: list[torch.Tensor] = []
+
+
+def zeroed_workspace(nbytes: int, device: torch.device) -> torch.Tensor | None:
+    if nbytes <= 0:
+        return None
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _ZEROED.get(idx)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ZEROED_RETIRED.append(buf)
+        size = max(int(nbytes), 2 * buf.numel() if buf is not None else 0, 1 << 24)
+        buf = torch.zeros(size, dtype=torch.uint8, device=device)
+        _ZEROED[idx] = buf
+    return buf
+
+
 def workspace(nbytes: int, device: torch.device) -> torch.Tensor | None:
     """Scratch allocated through torch's caching allocator (graph-safe, like the reference's
     ``torch.empty`` scratch in flashdecoding.py:350-358)."""

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from .._common import check, counters, lib, ptr, require_cuda, stream_handle, workspace
+from .._common import check, counters, lib, ptr, require_cuda, stream_handle, zeroed_workspace
 
 _Q_INT4 = 0
 
@@ -55,7 +55,7 @@ def w4a16_matmul(
         bias = bias.contiguous()
     L = lib()
     nbytes = L.b2l_quant_gemm_workspace_bytes(_Q_INT4, m, n, k, int(group_size))
-    ws = workspace(nbytes, x.device)
+    ws = zeroed_workspace(nbytes, x.device)
     cnt = counters(x.device)
     check(
         L.b2l_w4a16_matmul(
@@ -143,7 +143,7 @@ def w4a16_matmul_packed(x: torch.Tensor, packed: PackedW4, *, bias: torch.Tensor
         bias = bias.contiguous()
     L = lib()
     nbytes = L.b2l_quant_gemm_workspace_bytes(_Q_INT4, m, n, k, packed.group_size)
-    ws = workspace(nbytes, x.device)
+    ws = zeroed_workspace(nbytes, x.device)
     cnt = counters(x.device)
     check(
         L.b2l_w4a16_matmul_packed(

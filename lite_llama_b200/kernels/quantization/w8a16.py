@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from .._common import check, counters, lib, ptr, require_cuda, stream_handle, workspace
+from .._common import check, counters, lib, ptr, require_cuda, stream_handle, zeroed_workspace
 
 _Q_FP8, _Q_INT8 = 1, 2
 
@@ -55,7 +55,7 @@ def w8a16_matmul(
     L = lib()
     kind = _Q_FP8 if is_fp8 else _Q_INT8
     nbytes = L.b2l_quant_gemm_workspace_bytes(kind, m, n, k, int(group_k))
-    ws = workspace(nbytes, x.device)
+    ws = zeroed_workspace(nbytes, x.device)
     cnt = counters(x.device)
     check(
         L.b2l_w8a16_matmul(

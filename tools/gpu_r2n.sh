@@ -12,8 +12,11 @@ cp tools/variants/lib_tlite.so lite_llama_b200/libb200lite.so
 run tlite 200 python tools/tlite.py --shapes o:4096x4096,down:4096x14336,gate_up:28672x4096
 cp /tmp/lib_product.so lite_llama_b200/libb200lite.so
 [ -n "$BENCH" ] && run bench 200 python bench.py --steps 64 --warmup 4 --no-cpu-baseline
+[ -n "$STRESS" ] && run stress 500 python -m pytest -q -p no:cacheprovider -x tests/test_stress_gpu.py -m gpu
+[ -n "$STRESS" ] && run host 400 python -m pytest -q -p no:cacheprovider -x --timeout 120 tests/test_host_gpu.py -m gpu
 cat $S
 tail -n 3 gpurun_out/r2n_tests.out
 cat gpurun_out/r2n_probe.out | cut -c1-200
+[ -n "$STRESS" ] && tail -n 3 gpurun_out/r2n_stress.out gpurun_out/r2n_host.out
 [ -n "$BENCH" ] && grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*' gpurun_out/r2n_bench.out | head -4
 cat gpurun_out/r2n_tlite.out

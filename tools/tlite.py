@@ -19,8 +19,8 @@ NAMES = {23: "first instruction", 24: "producer lane: reached its set-up", 25: "
          4: "mma0: first activations landed", 5: "mma0: first block issued", 12: "epilogue: first segment complete",
          10: "dequant g0: last block stored", 11: "dequant g1: last block stored", 6: "mma0: last block issued",
          7: "mma1: last block issued", 13: "epilogue: last segment drained", 14: "epilogue: tile stored / ticket taken",
-         15: "final barrier passed", 27: "fix-up: first tile summed", 20: "fix-up done (exit)"}
-ORDER = [23, 0, 24, 25, 26, 19, 1, 2, 3, 8, 9, 4, 5, 12, 10, 11, 6, 7, 13, 14, 15, 27, 20]
+         15: "final barrier passed", 28: "fix-up: own partial read, polling starts", 30: "fix-up: first batch of loads back", 27: "fix-up: first tile summed", 20: "fix-up done (exit)"}
+ORDER = [23, 0, 24, 25, 26, 19, 1, 2, 3, 8, 9, 4, 5, 12, 10, 11, 6, 7, 13, 14, 15, 28, 30, 27, 20]
 
 
 def main():
@@ -78,7 +78,7 @@ def main():
             tot_cyc = int(t[c, 20] - t[c, 0])
             sc = int(t[c, 17] - t[c, 16]) / tot_cyc
             row = " ".join(f"{NAMES[i].split(':')[0][:10]}#{i}={int((t[c, i] - t[c, 0]) * sc)}" for i in ORDER if t[c, i] != 0 and i not in (0, 23, 24, 25, 26))
-            print(f"     cta {c} rb={int(t[c, 22])} nfix={int(t[c, 21])}: {row}")
+            print(f"     cta {c} rb={int(t[c, 22])} nfix={int(t[c, 21])} failed polls={int(t[c, 29])}: {row}")
 
 
 if __name__ == "__main__":
