@@ -343,6 +343,7 @@ def main() -> None:
     from lite_llama_b200 import _lib
     from lite_llama_b200.executor import ModelRunner
     from lite_llama_b200.executor.model_runner import GreedyDecodeLoop
+    from lite_llama_b200.kernels import argmax_rows
 
     lib = _lib.load()
     B, P, K, W = args.batch, args.prompt_len, args.steps, args.warmup
@@ -435,7 +436,7 @@ def main() -> None:
         ids_dev.copy_(host_in, non_blocking=True)                      # H2D: this step's input token ids
         runner.decode_alloc_kv_cache(B)                                # reserve rows, bump lengths, update the table
         logits = runner.forward(ids_dev, pos)                          # public API (captured decode graph)
-        nxt = logits[:, -1].argmax(-1)
+        nxt = argmax_rows(logits[:, -1, :])                            # greedy sampling (library kernel, first-index ties like torch)
         host_out.copy_(nxt, non_blocking=True)                         # D2H: sampled tokens
         torch.cuda.current_stream().synchronize()
         host_in.copy_(host_out.view(B, 1))                             # the host feeds the next step
