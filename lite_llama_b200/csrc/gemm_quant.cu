@@ -915,12 +915,14 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
           for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
           tc_wait_ld();
+#ifndef B2L_FIX_B
           if (c0 + CH == BT) {
             // the accumulator is in registers: hand the buffer back before doing the arithmetic
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
           }
+#endif
           if (QK == Q_INT4 && need_xsum) {
 #pragma unroll
             for (int j4 = 0; j4 < CH / 4; ++j4) {
@@ -936,6 +938,11 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             for (int j = 0; j < CH; ++j) acc[c0 + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c0 + j]);
           }
         }
+#ifdef B2L_FIX_B
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+#endif
         if (warp == kWarpEpi0) TL_STAMP(TL_EPI_DONE, seg);
         k_pos = k_next;
         k_group_end += seg_len;
@@ -1099,9 +1106,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       uint4 raw[8];                                          // the row's 128 raw bytes (8 swizzled 16-byte chunks)
 #pragma unroll
       for (int c = 0; c < 8; ++c) raw[c] = lds_128(rawrow + ((c ^ rx) << 4));
-      // the raw bytes are in registers: hand the weight stage back to the TMA producer right away
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->w_empty[rstage]);
+      // The weight stage is handed back to the TMA producer at the END of this block, not here: at this point the
+      // loads have been issued, not returned, and nothing that follows depends on them until the conversion --
+      // a refill that found its weights in L2 could land in the stage first (rows are written in order, so the
+      // lowest rows of a tile were the ones hit).  Found in round 2 by tests/test_kernels_gpu.py::
+      // test_w4a16_streamk_back_to_back_launches_are_isolated at 33-64 tokens: ~10 % of the launches over a long-K
+      // shape had one or a few output columns off by one scale group's contribution (tools/nondet_probe.py).
       if (quad == 0) TL_STAMP(TL_DQ_START, rb);
       if (warp == 0 && lane == 0 && rb == 0) LT(8);
       // one operand sub-stage per 64-element sub-block; the "sub-block ready" arrive of sub-block s is issued
@@ -1187,6 +1197,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           if (tls) tls[3] = clock64();
           if (!(debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 64 + (sub & 1) * 32, vals);
           else asm volatile("" ::"r"(vals[0] ^ vals[7] ^ vals[13] ^ vals[31]));
+#ifdef B2L_FIX_A
+          tc_wait_st();
+#endif
           if (tls) tls[4] = clock64();
           if ((sub & 1) == 1 || gsub == nsub_total - 1) pending = ostage;
         }
@@ -1197,6 +1210,9 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->op_full[pending]);
       }
+      // every raw word has been converted: the stage can be refilled
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->w_empty[rstage]);
       if (quad == 0) TL_STAMP(TL_DQ_DONE, rb);
       if (warp == 0 && lane == 0 && rb == 0) LT(9);
       if (quad == 0 && lane == 0 && rb + 2 >= nrb) LT(10 + half);
@@ -1246,11 +1262,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int s0 = 1; s0 < sharers; s0 += SB) {
           uint32_t v[SB][NJ];
           unsigned long long t0 = 0ull;
-          for (bool first = true;; first = false) {
-            // All requests first, the tag bits afterwards.  The first attempt uses ordinary loads (this SM has not
-            // touched these lines during the launch, L1 is clean); a retry must not be served by L1 and uses gpu-scope
-            // loads -- it was never needed in the measured runs: the reducer's tile is its last piece and the other
-            // sharers are done by then.
+          for (;;) {
+            // All requests first, the tag bits afterwards.  gpu-scope loads (served by L2, never by L1): the same
+            // workspace words are read by whichever CTA reduces this tile in the NEXT launch, possibly on this very SM,
+            // and L1 is not invalidated between programmatically dependent launches -- an ordinary load could return
+            // the previous launch's tagged words.  (Ordinary loads were not faster: the ~1.3 us is latency.)  A retry
+            // was never needed in the measured runs: the reducer's tile is its last piece.
 #pragma unroll
             for (int u = 0; u < SB; ++u) {
               const bool on = s0 + u < sharers;
@@ -1258,10 +1275,7 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               for (int i = 0; i < NJ; ++i) {
                 uint32_t w = 1u;                                   // a slot past the last sharer counts as "there"
                 const uint32_t* src = base + (size_t)(s0 + u) * (BT * kBlockW) + (j_first + i * JT) * kBlockW;
-                if (on) {
-                  if (first) asm volatile("ld.global.u32 %0, [%1];" : "=r"(w) : "l"(src) : "memory");
-                  else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(src) : "memory");
-                }
+                if (on) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(src) : "memory");
                 v[u][i] = w;
               }
             }
@@ -1426,7 +1440,10 @@ static inline void quant_rings(int qk, SplitPlan& pl, int blocks, int max_groups
 static inline SplitPlan quant_plan(int qk, int64_t M, int64_t N, int64_t K, int seg_len) {
   // token tile capped at 64: the epilogue keeps the running fp32 accumulator in registers
   SplitPlan pl;
-  const int64_t mt = M > 64 ? 64 : M;
+#ifndef B2L_QUANT_BT_CAP
+#define B2L_QUANT_BT_CAP 64
+#endif
+  const int64_t mt = M > B2L_QUANT_BT_CAP ? B2L_QUANT_BT_CAP : M;
   pl.bt = pick_bt(mt);
   pl.n_tiles = (int)cdiv64(N, kBlockW);
   pl.m_tiles = (int)cdiv64(M, pl.bt);

@@ -13,6 +13,7 @@ Tolerances (stated per op, always tighter than or equal to the reference's own t
 from __future__ import annotations
 
 import math
+import os
 
 import pytest
 import torch
@@ -1019,3 +1020,35 @@ def test_argmax_rows_matches_torch_and_breaks_ties_low():
     t[0, 100] = t[0, 3000] = 5.0
     t[1, 4095] = 1.0
     assert K().argmax_rows(t).tolist() == [100, 4095]
+
+
+@pytest.mark.parametrize("m", [32, 36, 1])
+@pytest.mark.parametrize("n,k", [(4096, 4096), (6144, 4096), (4096, 14336), (3072, 4096), (4096, 2048), (4096, 7168),
+                                 (14336, 4096)])
+def test_w4a16_streamk_back_to_back_launches_are_isolated(m, n, k):
+    """Stream-K tiles are handed over through a persistent workspace with flag-in-data words that every launch must
+    leave clean (csrc/gemm_quant.cu).  Same-shaped launches reuse the very same words: run a chain of launches over
+    DIFFERENT weights without synchronising (PDL overlaps them) and require every result to be bit-identical to the
+    one the same call gives in isolation -- a launch that picked up a predecessor's partial sums (stale cache line,
+    word not cleared) would differ by whole tiles."""
+    torch.manual_seed(7)
+    g = 128
+    x = (torch.randn(m, k, device="cuda", dtype=torch.float16) * 0.5)
+    packed = []
+    for i in range(6):
+        qw = torch.randint(-(2**31), 2**31 - 1, (n, k // 8), device="cuda", dtype=torch.int64).to(torch.int32)
+        sc = torch.rand(n, k // g, device="cuda") * 0.01 + 0.001
+        zp = torch.randint(0, 16, (n, k // g), device="cuda").float()
+        packed.append(K().w4a16_pack(qw, sc, zp, group_size=g))
+    alone = []
+    for pk in packed:
+        torch.cuda.synchronize()
+        torch.zeros(1 << 22, device="cuda").add_(1.0)          # another kernel in between
+        torch.cuda.synchronize()
+        alone.append(K().w4a16_matmul_packed(x, pk).clone())
+    torch.cuda.synchronize()
+    for rep in range(int(os.environ.get("B2L_TEST_REPS", "20"))):
+        outs = [K().w4a16_matmul_packed(x, pk) for pk in packed]   # back to back, no synchronisation
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip(alone, outs)):
+            assert torch.equal(a, b), f"repetition {rep}, launch {i}: result differs from the isolated call"

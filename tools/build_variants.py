@@ -20,6 +20,10 @@ VARIANTS = {
     "order1_spin_lat": ["-DB2L_DQ_ORDER=1", "-DB2L_QWAIT_LAT_MODE=1"],
     "order1_short": ["-DB2L_DQ_ORDER=1", "-DB2L_QWAIT_MODE=2"],
     "tlite": ["-DB2L_TLITE=1"],
+    "fixA": ["-DB2L_FIX_A=1"],
+    "fixB": ["-DB2L_FIX_B=1"],
+    "fixD": ["-DB2L_FIX_D=1"],
+    "cap32": ["-DB2L_QUANT_BT_CAP=32"],
 }
 
 
@@ -29,10 +33,16 @@ def main():
     out_dir = ROOT / "tools" / "variants"
     out_dir.mkdir(exist_ok=True)
     others = [str(o) for o in sorted(B.OBJ_DIR.glob("*.o")) if o.stem != "gemm_quant"]
+    procs = []
     for name in names:
         obj = out_dir / f"gemm_quant_{name}.o"
         cmd = [B._nvcc(), *B.NVCC_FLAGS, *VARIANTS[name], "-c", str(B.CSRC / "gemm_quant.cu"), "-o", str(obj)]
-        subprocess.run(cmd, check=True)
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("variant compile failed")
+    for name in names:
+        obj = out_dir / f"gemm_quant_{name}.o"
         lib = out_dir / f"lib_{name}.so"
         subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
                         "-o", str(lib), str(obj), *others], check=True)
