@@ -192,6 +192,13 @@ int b2l_w8a16_matmul(void* y, const void* x, const void* qweight, int weight_is_
  * is two calls: per-token dynamic quantisation (w8a8.py:35-68), then the int8 GEMM (w8a8.py:75-130). */
 int b2l_quantize_activations_int8(void* q, void* scales, const void* x, int64_t m, int64_t k, int64_t x_row_stride,
                                   int64_t q_row_stride, int dtype, void* stream);
+/* skip_rmsnorm (skip_rmsnorm.py:192-234) followed by the per-token quantisation above (w8a8.py:35-68) in one
+ * launch, for a norm whose only consumer is an int8 GEMM (models/base.py:307-312 under SmoothQuant): q / scales
+ * are bit-identical to b2l_skip_rmsnorm + b2l_quantize_activations_int8; the fp16 norm output is never written.
+ * Needs n % 8 == 0, n <= 16384, 16-byte aligned rows. */
+int b2l_skip_rmsnorm_quant_int8(void* q, void* scales, const void* x, void* residual, const void* weight,
+                                int64_t rows, int64_t n, int64_t x_row_stride, int64_t r_row_stride,
+                                int64_t q_row_stride, float eps, int dtype, void* stream);
 int b2l_w8a8_gemm(void* y, const void* xq, const void* wq, const void* a_scale, const void* b_scale,
                   const void* bias_f32, int64_t m, int64_t n, int64_t k, int64_t xq_row_stride,
                   int64_t wq_row_stride, int64_t y_row_stride, void* workspace, int64_t workspace_bytes,

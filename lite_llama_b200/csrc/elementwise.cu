@@ -633,6 +633,144 @@ extern "C" int b2l_quantize_activations_int8(void* q, void* scales, const void* 
 }
 
 // --------------------------------------------------------------------------- //
+// skip_rmsnorm + per-token int8 quantisation in one launch (SmoothQuant decoder: the norm output feeds exactly one
+// int8 GEMM -- models/base.py:307-312 -> quantization/methods/w8a8.py -> kernels/quantization/w8a8.py:35-68).
+// Same arithmetic as skip_rmsnorm_block_kernel followed by quantize_act_int8_kernel on its fp16 output (the rounded
+// norm output is what gets quantised), so q / scales are bit-identical to the two-launch path; y is never written.
+// --------------------------------------------------------------------------- //
+template <typename T, int VPT_MAX>
+__global__ void __launch_bounds__(512) skip_rmsnorm_quant_kernel(int8_t* __restrict__ q, float* __restrict__ scales,
+                                                                 const T* __restrict__ x, T* __restrict__ res,
+                                                                 const T* __restrict__ w, int64_t n, int64_t x_stride,
+                                                                 int64_t r_stride, int64_t q_stride, float eps) {
+  pdl_prologue();
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * x_stride;
+  T* rr = res ? res + row * r_stride : nullptr;
+  int8_t* qr = q + row * q_stride;
+  const int nchunks = (int)(n / 8);
+  float vals[VPT_MAX][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT_MAX; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < nchunks) {
+      uint4 xv = ldg_128(xr + c * 8);
+      const T* xe = reinterpret_cast<const T*>(&xv);
+      if (rr) {
+        uint4 rv = ldg_128(rr + c * 8);
+        const T* re = reinterpret_cast<const T*>(&rv);
+        uint4 ov;
+        T* oe = reinterpret_cast<T*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float s = to_f32(xe[j]) + to_f32(re[j]);
+          vals[i][j] = s;
+          oe[j] = from_f32<T>(s);
+        }
+        stg_128(rr + c * 8, ov);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vals[i][j] = to_f32(xe[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += vals[i][j] * vals[i][j];
+    }
+  }
+  __shared__ float red[16];
+  __shared__ float red_max[16];
+  ss = warp_reduce_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) tot += red[i];
+  const float rrms = div_full(1.0f, sqrt_approx(tot / (float)n + eps));
+  // the norm output, rounded to the activation dtype exactly like the stand-alone kernel, stays in registers
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT_MAX; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < nchunks) {
+      uint4 wv = ldg_128(w + c * 8);
+      const T* we = reinterpret_cast<const T*>(&wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        T nrm = from_f32<T>(vals[i][j] * rrms);
+        const float out = to_f32(from_f32<T>(to_f32(nrm) * to_f32(we[j])));
+        vals[i][j] = out;
+        amax = fmaxf(amax, fabsf(out));
+      }
+    }
+  }
+  amax = warp_reduce_max(amax);
+  if ((threadIdx.x & 31) == 0) red_max[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  float m = 0.f;
+  for (int i = 0; i < nw; ++i) m = fmaxf(m, red_max[i]);
+  float scale = div_full(m, 127.0f);
+  scale = scale > 0.f ? scale : 1.0f;
+#pragma unroll
+  for (int i = 0; i < VPT_MAX; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < nchunks) {
+      uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int32_t iv;
+        asm("cvt.rzi.s32.f32 %0, %1;" : "=r"(iv) : "f"(div_full(vals[i][j], scale)));   // Triton's fp32 -> int8 cast
+        const uint32_t b = (uint32_t)(uint8_t)(int8_t)iv;
+        if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
+      }
+      *reinterpret_cast<uint2*>(qr + c * 8) = make_uint2(lo, hi);
+    }
+  }
+  if (threadIdx.x == 0) scales[row] = scale;
+}
+
+template <typename T>
+static int launch_skip_rmsnorm_quant(void* q, void* scales, const void* x, void* res, const void* w, int64_t rows,
+                                     int64_t n, int64_t xs, int64_t rs, int64_t qs, float eps, cudaStream_t st) {
+  if (rows == 0) return B2L_OK;
+  const bool aligned = (n % 8 == 0) && (xs % 8 == 0) && (res == nullptr || rs % 8 == 0) && (qs % 8 == 0) &&
+                       ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && (res == nullptr || (uintptr_t)res % 16 == 0) &&
+                       ((uintptr_t)q % 8 == 0);
+  B2L_REQUIRE(aligned && n / 8 <= 8 * 256, "skip_rmsnorm_quant_int8: needs n %% 8 == 0, n <= 16384 and 16-byte aligned rows (n=%lld)",
+              (long long)n);
+  int threads = 256;
+  const int64_t chunks = n / 8;
+  if (chunks <= 128) threads = 128;
+  else if (chunks <= 512 && chunks > 256) threads = 512;
+  const int vpt = (int)cdiv64(chunks, threads);
+  int8_t* qq = (int8_t*)q; float* ss = (float*)scales; const T* xx = (const T*)x; T* rr = (T*)res; const T* ww = (const T*)w;
+  if (vpt <= 1)
+    b2l_launch(skip_rmsnorm_quant_kernel<T, 1>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, qq, ss, xx, rr, ww, n, xs, rs, qs, eps);
+  else if (vpt <= 2)
+    b2l_launch(skip_rmsnorm_quant_kernel<T, 2>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, qq, ss, xx, rr, ww, n, xs, rs, qs, eps);
+  else if (vpt <= 4)
+    b2l_launch(skip_rmsnorm_quant_kernel<T, 4>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, qq, ss, xx, rr, ww, n, xs, rs, qs, eps);
+  else
+    b2l_launch(skip_rmsnorm_quant_kernel<T, 8>, dim3((unsigned)rows), dim3(threads), (size_t)(0), st, qq, ss, xx, rr, ww, n, xs, rs, qs, eps);
+  B2L_LAUNCH_CHECK();
+  return B2L_OK;
+}
+
+extern "C" int b2l_skip_rmsnorm_quant_int8(void* q, void* scales, const void* x, void* residual, const void* weight,
+                                           int64_t rows, int64_t n, int64_t x_row_stride, int64_t r_row_stride,
+                                           int64_t q_row_stride, float eps, int dtype, void* stream) {
+  B2L_REQUIRE(q && scales && x && weight, "skip_rmsnorm_quant_int8: null pointer");
+  B2L_REQUIRE(rows >= 0 && n > 0, "skip_rmsnorm_quant_int8: bad shape rows=%lld n=%lld", (long long)rows, (long long)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2L_F16)
+    return launch_skip_rmsnorm_quant<__half>(q, scales, x, residual, weight, rows, n, x_row_stride, r_row_stride,
+                                             q_row_stride, eps, st);
+  if (dtype == B2L_BF16)
+    return launch_skip_rmsnorm_quant<__nv_bfloat16>(q, scales, x, residual, weight, rows, n, x_row_stride, r_row_stride,
+                                                    q_row_stride, eps, st);
+  B2L_UNSUPPORTED("skip_rmsnorm_quant_int8: dtype %d", dtype);
+}
+
+// --------------------------------------------------------------------------- //
 // moe_sum (reference: lite_llama/kernels/fused_moe.py:316-333)
 //   out[m, :] = sum_k in[m*top_k + k, :]   (fp32 accumulate, in slot order)
 // --------------------------------------------------------------------------- //

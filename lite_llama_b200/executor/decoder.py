@@ -16,6 +16,7 @@ o/down on the contracted dim, one SUM all-reduce after o_proj and after down_pro
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -33,12 +34,16 @@ from ..kernels import (
     swiglu_forward,
     update_kv_buffer,
 )
+from ..kernels.quantization import smoothquant_matmul_prequant
+from ..kernels.skip_rmsnorm import can_fuse_int8_quant, skip_rmsnorm_quant_int8
 from ..kernels.tp_fused import allreduce_skip_rmsnorm
 from ..quantization import LinearWeights, apply_linear, make_linear_weights
 from ..quantization.params import quantize_fp8_blockwise, reblock_scales
 from .model_config import ModelConfig
 
 _LOG2E = 1.4426950408889634
+# SmoothQuant: fold the per-token int8 quantisation into the norm that feeds the GEMM (B2L_FUSE_NORM_QUANT=0: two launches)
+_FUSE_NORM_QUANT = os.environ.get("B2L_FUSE_NORM_QUANT", "1") != "0"
 
 
 @dataclass
@@ -233,13 +238,9 @@ class Decoder:
         per-rank PARTIAL under tensor parallelism: its all-reduce (linear.py:160-161) is fused into this layer's
         input norm, the o_proj one into the post-attention norm (kernels/tp_fused.py)."""
         eps = self.cfg.rms_norm_eps
-        if residual is None:
-            hidden, residual = skip_rmsnorm(hidden, residual, lw.input_norm, eps)      # base.py:307
-        else:
-            hidden, residual = allreduce_skip_rmsnorm(hidden, residual, lw.input_norm, eps)
         tokens = batch * seq_len
-        x = hidden.view(tokens, self.cfg.hidden_size)
-        qkv = apply_linear(x, lw.qkv)                                                   # base.py:213-215
+        # input norm (base.py:307) -> fused q|k|v projection (base.py:213-215)
+        qkv, residual = self._norm_linear(hidden, residual, lw.input_norm, lw.qkv, eps, tokens)
         xq = qkv[:, : self.q_size].view(tokens, self.num_heads, self.head_dim)
         xk = qkv[:, self.q_size : self.q_size + self.kv_size].view(tokens, self.num_kv_heads, self.head_dim)
         xv = qkv[:, self.q_size + self.kv_size :].view(tokens, self.num_kv_heads, self.head_dim)
@@ -264,15 +265,32 @@ class Decoder:
                                   atten_info.b_seq_len, atten_info.max_actual_seq_len)
         o = apply_linear(attn.view(tokens, self.q_size), lw.o)                          # base.py:245 (partial)
         # all-reduce (linear.py:160-161) + residual add + post-attention norm (base.py:312) in one kernel
-        hidden, residual = allreduce_skip_rmsnorm(o.view(batch, seq_len, -1), residual, lw.post_norm, eps)
         if lw.moe is not None:
+            hidden, residual = allreduce_skip_rmsnorm(o.view(batch, seq_len, -1), residual, lw.post_norm, eps)
             down = self._moe(hidden.view(tokens, -1), lw.moe)                           # qwen3_moe.py:102-111 (partial)
             return down.view(batch, seq_len, -1), residual
-        gu = apply_linear(hidden.view(tokens, -1), lw.gate_up)                          # base.py:263-264
+        gu, residual = self._norm_linear(o.view(batch, seq_len, -1), residual, lw.post_norm, lw.gate_up, eps, tokens)  # base.py:263-264
         # W4A16: the activation already ran in the GEMM epilogue (row-interleaved gate|up), gu is [tokens, inter]
         act = gu if lw.gate_up.swiglu else swiglu_forward(gu[:, : self.inter], gu[:, self.inter :])
         down = apply_linear(act, lw.down)                                               # partial: reduced by the next norm
         return down.view(batch, seq_len, -1), residual
+
+    @staticmethod
+    def _norm_linear(hidden, residual, norm_weight, w: LinearWeights, eps: float, tokens: int):
+        """``skip_rmsnorm`` (with the pending tensor-parallel all-reduce of ``hidden`` when there is one) followed by the
+        projection that consumes it; returns ``(projection [tokens, out], residual)``. SmoothQuant (TP = 1): the norm
+        kernel also does the per-token int8 quantisation the GEMM needs (reference: two more launches and an fp16 round
+        trip per norm, quantization/w8a8.py:35-68) -- the quantised activations are bit-identical to the unfused path."""
+        n = hidden.shape[-1]
+        if (w.method == "smoothquant" and _FUSE_NORM_QUANT and get_tp_world_size() <= 1 and can_fuse_int8_quant(n)
+                and hidden.dtype == torch.float16):
+            q, s, residual = skip_rmsnorm_quant_int8(hidden, residual, norm_weight, eps)
+            return smoothquant_matmul_prequant(q, s, w.qweight, w.scales, bias=w.bias, out_dtype=hidden.dtype), residual
+        if residual is None:
+            hidden, residual = skip_rmsnorm(hidden, residual, norm_weight, eps)
+        else:
+            hidden, residual = allreduce_skip_rmsnorm(hidden, residual, norm_weight, eps)
+        return apply_linear(hidden.view(tokens, n), w), residual
 
     @staticmethod
     def _moe(x: torch.Tensor, m: MoeWeights) -> torch.Tensor:

@@ -240,3 +240,34 @@ def test_one_llama3_8b_shape_layer_matches_the_cpu_restatement():
             _check_logits(out, ref1, tol=4e-2)
             tok = ref1[:, -1].argmax(-1)
         del runner
+
+
+def test_smoothquant_fused_norm_quant_changes_no_logit():
+    """The SmoothQuant decoder folds the activation quantisation into the norm kernels (executor/decoder.py::_norm_linear):
+    logits of a prefill + decode step must be bit-identical to the two-launch path."""
+    from lite_llama_b200.executor import decoder as dec
+
+    def run(fused: bool):
+        old = dec._FUSE_NORM_QUANT
+        dec._FUSE_NORM_QUANT = fused
+        try:
+            cfg, runner, _ = _build("tiny-qwen3", "smoothquant")
+            B, P = 3, 12
+            lens = torch.tensor([12, 7, 9]).cuda()
+            g = torch.Generator().manual_seed(0)
+            ids = torch.randint(0, cfg.vocab_size, (B, P), generator=g).cuda()
+            pos = torch.arange(P).repeat(B, 1).cuda()
+            runner.prefill_alloc_kv_cache(P, lens, torch.arange(B).cuda())
+            pre = runner.forward(ids, pos).clone()
+            nxt = pre[torch.arange(B).cuda(), lens - 1].argmax(-1)
+            runner.decode_alloc_kv_cache(B)
+            dec_logits = runner.forward(nxt.view(B, 1), lens.view(B, 1)).clone()
+            return pre, dec_logits, lens
+        finally:
+            dec._FUSE_NORM_QUANT = old
+
+    p1, d1, lens = run(True)
+    p0, d0, _ = run(False)
+    for i in range(3):
+        assert torch.equal(p1[i, : lens[i]], p0[i, : lens[i]])
+    assert torch.equal(d1, d0)

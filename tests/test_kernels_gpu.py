@@ -1052,3 +1052,40 @@ def test_w4a16_streamk_back_to_back_launches_are_isolated(m, n, k):
         torch.cuda.synchronize()
         for i, (a, b) in enumerate(zip(alone, outs)):
             assert torch.equal(a, b), f"repetition {rep}, launch {i}: result differs from the isolated call"
+
+
+@pytest.mark.parametrize("rows,n", [(1, 3584), (32, 4096), (256, 3584), (7, 896), (3, 128), (5, 8192)])
+@pytest.mark.parametrize("with_residual", [True, False])
+def test_skip_rmsnorm_quant_int8_is_the_two_ops_in_one_launch(rows, n, with_residual):
+    """SmoothQuant decoder: norm + per-token int8 quantisation fused (csrc/elementwise.cu). q, scales and the updated
+    residual must be bit-identical to skip_rmsnorm followed by quantize_activations_int8 (reference:
+    skip_rmsnorm.py:192-234, quantization/w8a8.py:35-68); the oracle pins the pair end to end."""
+    torch.manual_seed(rows * 131 + n)
+    x = torch.randn(rows, n, device="cuda", dtype=torch.float16)
+    res = torch.randn(rows, n, device="cuda", dtype=torch.float16) if with_residual else None
+    w = (torch.randn(n, device="cuda", dtype=torch.float16) * 0.1 + 1.0)
+    r1 = res.clone() if with_residual else None
+    y, r1o = K().skip_rmsnorm(x, r1, w, 1e-6)
+    q_ref, s_ref = K().quantize_activations_int8(y)
+    r2 = res.clone() if with_residual else None
+    q, s, r2o = K().skip_rmsnorm_quant_int8(x, r2, w, 1e-6)
+    assert torch.equal(q, q_ref) and torch.equal(s, s_ref)
+    assert torch.equal(r1o, r2o)
+    # against the CPU restatement of both ops
+    y_cpu, _ = ops.skip_rmsnorm(x.cpu(), res.cpu() if with_residual else None, w.cpu(), 1e-6)
+    q_cpu, s_cpu = ops.quantize_activations_int8(y_cpu)
+    torch.testing.assert_close(s.cpu(), s_cpu.float().view(-1), rtol=2e-3, atol=1e-6)
+    assert int((q.cpu().int() - q_cpu.int()).abs().max()) <= 1     # a 1-ulp difference of the fp16 norm output moves a step
+
+
+def test_smoothquant_prequant_gemm_is_the_second_half_of_smoothquant_matmul():
+    torch.manual_seed(3)
+    m, n, k = 48, 512, 896
+    x = torch.randn(m, k, device="cuda", dtype=torch.float16)
+    wq = torch.randint(-127, 128, (n, k), device="cuda", dtype=torch.int8)
+    ws = torch.rand(n, device="cuda") * 0.01
+    bias = torch.randn(n, device="cuda")
+    full = K().smoothquant_matmul(x, wq, ws, bias=bias)
+    qa, sa = K().quantize_activations_int8(x)
+    half = K().smoothquant_matmul_prequant(qa, sa, wq, ws, bias=bias, out_dtype=torch.float16)
+    assert torch.equal(full, half)
