@@ -139,6 +139,20 @@ def test_stream_k_partition_arithmetic():
                 assert 0 <= lo < hi <= nrb_tile
                 blocks += hi - lo
             assert blocks == g1 - g0
+            # what the flag-in-data hand-over of shared tiles relies on (csrc/gemm_quant.cu, epilogue + end of kernel):
+            # at most two pieces of a range are shared (its first and its last tile), and a CTA that is slot 0 of a
+            # shared tile -- the tile's reducer -- meets that tile as the LAST piece of its range (so its weight ring is
+            # idle when it parks its own partial sum there, and it reduces at most one tile)
+            shared = []
+            for i in range(npieces):
+                t = t0 + i
+                c_lo, c_hi = owner(t * nrb_tile, ctas, total), owner((t + 1) * nrb_tile - 1, ctas, total)
+                assert c_lo <= c <= c_hi
+                if c_hi > c_lo:
+                    shared.append(i)
+                    if c == c_lo:
+                        assert i == npieces - 1, "the reducer's tile must be the last piece of its range"
+            assert len(shared) <= 2 and all(i in (0, npieces - 1) for i in shared)
         assert all(v == 1 for v in cover)
         return max(owner((t + 1) * nrb_tile - 1, ctas, total) - owner(t * nrb_tile, ctas, total) + 1
                    for t in range(n_tiles))
