@@ -915,14 +915,12 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
           for (int c = 0; c < CH; c += 16) tmem_ld_32x32b_x16(ta + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(pv + c));
           tc_wait_ld();
-#ifndef B2L_FIX_B
           if (c0 + CH == BT) {
             // the accumulator is in registers: hand the buffer back before doing the arithmetic
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
           }
-#endif
           if (QK == Q_INT4 && need_xsum) {
 #pragma unroll
             for (int j4 = 0; j4 < CH / 4; ++j4) {
@@ -938,11 +936,6 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             for (int j = 0; j < CH; ++j) acc[c0 + j] = fmaf(sc, __uint_as_float(pv[j]), acc[c0 + j]);
           }
         }
-#ifdef B2L_FIX_B
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
-#endif
         if (warp == kWarpEpi0) TL_STAMP(TL_EPI_DONE, seg);
         k_pos = k_next;
         k_group_end += seg_len;
@@ -1197,9 +1190,6 @@ gemm_quant_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           if (tls) tls[3] = clock64();
           if (!(debug & DBG_NO_STTM)) tmem_st_32x32b_x32(lane_base + kAColBase + ostage * 64 + (sub & 1) * 32, vals);
           else asm volatile("" ::"r"(vals[0] ^ vals[7] ^ vals[13] ^ vals[31]));
-#ifdef B2L_FIX_A
-          tc_wait_st();
-#endif
           if (tls) tls[4] = clock64();
           if ((sub & 1) == 1 || gsub == nsub_total - 1) pending = ostage;
         }

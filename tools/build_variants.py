@@ -20,9 +20,6 @@ VARIANTS = {
     "order1_spin_lat": ["-DB2L_DQ_ORDER=1", "-DB2L_QWAIT_LAT_MODE=1"],
     "order1_short": ["-DB2L_DQ_ORDER=1", "-DB2L_QWAIT_MODE=2"],
     "tlite": ["-DB2L_TLITE=1"],
-    "fixA": ["-DB2L_FIX_A=1"],
-    "fixB": ["-DB2L_FIX_B=1"],
-    "fixD": ["-DB2L_FIX_D=1"],
     "cap32": ["-DB2L_QUANT_BT_CAP=32"],
 }
 
